@@ -1,0 +1,142 @@
+/*
+ * api_bcsr.c -- plain-C host layer: the reference's BCSR entry points (include/sparse/bcsr.h; reference
+ * sparse/bcsr.h:14-39) on top of the device-level C-ABI.  W is passed by value like the reference does; the device
+ * mirror is found through W.b_values (the caller owns and free()s the arrays, test/test_bcsr.cpp:48-51).
+ */
+#include <pthread.h>
+#include <stdlib.h>
+
+#include "sparse/bcsr.h"
+#include "tsg_host_shim.h"
+#include "tsgemm_b200.h"
+
+typedef struct {
+    const float *values; /* key */
+    const int *row_start, *col_idx;
+    int r, c, br, bc, k;
+    tsg_bcsr *dev;
+} bmirror;
+
+static bmirror *g_tab = NULL;
+static size_t g_len = 0, g_cap = 0;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int b_insert(const bcsr_t *W, tsg_bcsr *dev) {
+    if (g_len == g_cap) {
+        size_t ncap = g_cap ? 2 * g_cap : 16;
+        bmirror *nt = (bmirror *)realloc(g_tab, ncap * sizeof *nt);
+        if (!nt) return TSG_ENOMEM;
+        g_tab = nt;
+        g_cap = ncap;
+    }
+    bmirror e = {W->b_values, W->b_row_start, W->b_col_idx, W->r, W->c, W->br, W->bc, W->k, dev};
+    g_tab[g_len++] = e;
+    return TSG_OK;
+}
+
+static tsg_bcsr *b_mirror_of(const bcsr_t *W) {
+    tsg_bcsr *dev = NULL, *stale = NULL;
+    pthread_mutex_lock(&g_mu);
+    for (size_t i = 0; i < g_len; ++i)
+        if (g_tab[i].values == W->b_values) {
+            const bmirror *e = &g_tab[i];
+            if (e->row_start == W->b_row_start && e->col_idx == W->b_col_idx && e->r == W->r && e->c == W->c && e->br == W->br &&
+                e->bc == W->bc && e->k == W->k)
+                dev = e->dev;
+            else { stale = e->dev; g_tab[i] = g_tab[--g_len]; }
+            break;
+        }
+    if (!dev) {
+        if (tsg_bcsr_from_arrays(W->b_row_start, W->b_col_idx, W->b_values, W->r, W->c, W->br, W->bc, W->k, &dev) == TSG_OK) {
+            if (b_insert(W, dev) != TSG_OK) { tsg_bcsr_destroy(dev); dev = NULL; }
+        } else dev = NULL;
+    }
+    pthread_mutex_unlock(&g_mu);
+    if (stale) tsg_bcsr_destroy(stale);
+    return dev;
+}
+
+void bcsr_release_device(const bcsr_t *W) {
+    if (!W) return;
+    tsg_bcsr *dev = NULL;
+    pthread_mutex_lock(&g_mu);
+    for (size_t i = 0; i < g_len; ++i)
+        if (g_tab[i].values == W->b_values) {
+            dev = g_tab[i].dev;
+            g_tab[i] = g_tab[--g_len];
+            break;
+        }
+    pthread_mutex_unlock(&g_mu);
+    if (dev) tsg_bcsr_destroy(dev);
+}
+
+static size_t round32(size_t n) { return (n + 31) & ~(size_t)31; }
+
+bcsr_t *bcsr_from_dense(dense_t dense, int rows, int cols, int r, int c) { /* bcsr.c:19-139 */
+    tsg_clear_error();
+    if (rows < 0 || cols < 0 || r <= 0 || c <= 0) return NULL;
+    void *ddev = NULL;
+    int owned = 0;
+    tsg_bcsr *dev = NULL;
+    if (tsg_shim_stage_in(dense, (size_t)rows * (size_t)cols * sizeof(float), &ddev, &owned) != TSG_OK) return NULL;
+    int rc = tsg_bcsr_from_dense_f32((const float *)ddev, rows, cols, r, c, &dev);
+    tsg_shim_release(ddev, owned);
+    if (rc != TSG_OK) return NULL;
+    /* bcsr.c:14-17,74,88-90: every array comes from aligned_alloc(32, ...) and is released by the caller with free() */
+    bcsr_t *W = (bcsr_t *)aligned_alloc(32, round32(sizeof *W));
+    if (!W) { tsg_bcsr_destroy(dev); return NULL; }
+    tsg_bcsr_dims(dev, &W->r, &W->c, &W->br, &W->bc, &W->k);
+    W->b_values = (float *)aligned_alloc(32, round32((size_t)W->k * r * c * sizeof(float) + 1));
+    W->b_row_start = (int *)aligned_alloc(32, round32(((size_t)W->br + 1) * sizeof(int)));
+    W->b_col_idx = (int *)aligned_alloc(32, round32((size_t)W->k * sizeof(int) + 1));
+    int ok = W->b_values && W->b_row_start && W->b_col_idx;
+    if (ok) ok = tsg_bcsr_download(dev, W->b_row_start, W->b_col_idx, W->b_values) == TSG_OK;
+    if (ok) {
+        pthread_mutex_lock(&g_mu);
+        ok = b_insert(W, dev) == TSG_OK;
+        pthread_mutex_unlock(&g_mu);
+    }
+    if (!ok) {
+        free(W->b_values); free(W->b_row_start); free(W->b_col_idx); free(W);
+        tsg_bcsr_destroy(dev);
+        return NULL;
+    }
+    return W;
+}
+
+static void run_bcsr(const float *X, const bcsr_t *W, const float *B, float a, int use_prelu, float *Y, int M, int N, int K) {
+    tsg_clear_error();
+    if (M <= 0 || N <= 0) return;
+    tsg_bcsr *dev = b_mirror_of(W);
+    if (!dev) return;
+    void *dX = NULL, *dB = NULL, *dY = NULL;
+    int ox = 0, ob = 0, oy = 0;
+    if (tsg_shim_stage_in(X, (size_t)M * K * sizeof(float), &dX, &ox) != TSG_OK) return;
+    if (tsg_shim_stage_in(B, (size_t)N * sizeof(float), &dB, &ob) != TSG_OK) { tsg_shim_release(dX, ox); return; }
+    if (tsg_shim_stage_out_begin(Y, (size_t)M * N * sizeof(float), &dY, &oy) != TSG_OK) {
+        tsg_shim_release(dX, ox); tsg_shim_release(dB, ob);
+        return;
+    }
+    if (tsg_bcsr_gemm(dev, (const float *)dX, (const float *)dB, a, use_prelu, (float *)dY, M, N, K, N) == TSG_OK)
+        tsg_shim_stage_out_end(Y, (size_t)M * N * sizeof(float), dY, oy);
+    else
+        tsg_shim_release(dY, oy);
+    tsg_shim_release(dX, ox);
+    tsg_shim_release(dB, ob);
+}
+
+void bcsr_sgemm_basic(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
+    run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);
+}
+void bcsr_sgemm_prelu_basic(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, float a, dense_t __restrict Y, int M, int N, int K) {
+    run_bcsr(X, &W, B, a, 1, Y, M, N, K);
+}
+void bcsr_sgemm_avx(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
+    run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);
+}
+void bcsr_sgemm_prelu_avx(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, float a, dense_t __restrict Y, int M, int N, int K) {
+    run_bcsr(X, &W, B, a, 1, Y, M, N, K);
+}
+void bcsr_sgemm_avx2(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
+    run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);
+}

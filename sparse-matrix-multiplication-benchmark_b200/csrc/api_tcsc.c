@@ -1,0 +1,172 @@
+/*
+ * api_tcsc.c -- plain-C host layer: the reference's TCSC entry points (include/sparse/tcsc.h; reference
+ * sparse/tcsc.h:19-48) on top of the device-level C-ABI (include/tsgemm_b200.h).
+ *
+ * What happens here and nowhere else: argument conventions of the reference (host tcsc_t with malloc'ed arrays the
+ * caller may read, tcsc.c:22-33), the side table that remembers the device mirror of every tcsc_t this library
+ * handed out (or saw), and host<->device staging of X / B / Y.  No arithmetic happens on the CPU.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sparse/tcsc.h"
+#include "tsg_host_shim.h"
+#include "tsgemm_b200.h"
+
+/* ---- side table: tcsc_t* -> device mirror ------------------------------------------------------------------ */
+typedef struct {
+    const tcsc_t *host;
+    tsg_tcsc *dev;
+    /* fingerprint: a caller may free a tcsc_t and malloc may hand the same address out again */
+    int rows, cols, n_pos, n_neg;
+    const int *csp, *csn, *rip, *rin;
+} mirror_entry;
+
+static mirror_entry *g_tab = NULL;
+static size_t g_tab_len = 0, g_tab_cap = 0;
+static pthread_mutex_t g_tab_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int entry_matches(const mirror_entry *e, const tcsc_t *W) {
+    return e->host == W && e->rows == W->rows && e->cols == W->cols && e->n_pos == W->n_elem_pos && e->n_neg == W->n_elem_neg &&
+           e->csp == W->col_start_pos && e->csn == W->col_start_neg && e->rip == W->row_index_pos && e->rin == W->row_index_neg;
+}
+
+static int table_insert(const tcsc_t *W, tsg_tcsc *dev) {
+    if (g_tab_len == g_tab_cap) {
+        size_t ncap = g_tab_cap ? 2 * g_tab_cap : 16;
+        mirror_entry *nt = (mirror_entry *)realloc(g_tab, ncap * sizeof *nt);
+        if (!nt) return TSG_ENOMEM;
+        g_tab = nt;
+        g_tab_cap = ncap;
+    }
+    mirror_entry e = {W, dev, W->rows, W->cols, W->n_elem_pos, W->n_elem_neg,
+                      W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg};
+    g_tab[g_tab_len++] = e;
+    return TSG_OK;
+}
+
+static tsg_tcsc *table_remove(const tcsc_t *W) {
+    tsg_tcsc *dev = NULL;
+    pthread_mutex_lock(&g_tab_mu);
+    for (size_t i = 0; i < g_tab_len; ++i)
+        if (g_tab[i].host == W) {
+            dev = g_tab[i].dev;
+            g_tab[i] = g_tab[--g_tab_len];
+            break;
+        }
+    pthread_mutex_unlock(&g_tab_mu);
+    return dev;
+}
+
+/* mirror of W: cached, or (for a tcsc_t the caller assembled itself / a stale slot) built from W's host arrays */
+static tsg_tcsc *mirror_of(const tcsc_t *W) {
+    tsg_tcsc *dev = NULL, *stale = NULL;
+    pthread_mutex_lock(&g_tab_mu);
+    for (size_t i = 0; i < g_tab_len; ++i)
+        if (g_tab[i].host == W) {
+            if (entry_matches(&g_tab[i], W)) dev = g_tab[i].dev;
+            else { stale = g_tab[i].dev; g_tab[i] = g_tab[--g_tab_len]; }
+            break;
+        }
+    if (!dev) {
+        if (tsg_tcsc_from_arrays(W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg, W->rows, W->cols, &dev) == TSG_OK) {
+            if (table_insert(W, dev) != TSG_OK) { tsg_tcsc_destroy(dev); dev = NULL; }
+        } else dev = NULL;
+    }
+    pthread_mutex_unlock(&g_tab_mu);
+    if (stale) tsg_tcsc_destroy(stale);
+    return dev;
+}
+
+/* ---- builder (reference sparse/tcsc.c:6-66) ----------------------------------------------------------------- */
+tcsc_t *tcsc_from_dense(dense_t dense, int rows, int cols) {
+    tsg_clear_error();
+    void *ddev = NULL;
+    int owned = 0;
+    tsg_tcsc *dev = NULL;
+    if (rows < 0 || cols < 0) return NULL;
+    if (tsg_shim_stage_in(dense, (size_t)rows * (size_t)cols * sizeof(float), &ddev, &owned) != TSG_OK) return NULL;
+    int rc = tsg_tcsc_from_dense_f32((const float *)ddev, rows, cols, &dev);
+    tsg_shim_release(ddev, owned);
+    if (rc != TSG_OK) return NULL;
+
+    tcsc_t *W = (tcsc_t *)malloc(sizeof *W); /* tcsc.c:22 */
+    if (!W) { tsg_tcsc_destroy(dev); return NULL; }
+    W->rows = rows;
+    W->cols = cols;
+    tsg_tcsc_dims(dev, NULL, NULL, &W->n_elem_pos, &W->n_elem_neg);
+    /* tcsc.c:30-33 (malloc(0) may return NULL: ask for at least one int so NULL always means failure) */
+    W->col_start_pos = (int *)malloc(((size_t)cols + 1) * sizeof(int));
+    W->col_start_neg = (int *)malloc(((size_t)cols + 1) * sizeof(int));
+    W->row_index_pos = (int *)malloc(((size_t)W->n_elem_pos + 1) * sizeof(int));
+    W->row_index_neg = (int *)malloc(((size_t)W->n_elem_neg + 1) * sizeof(int));
+    int ok = W->col_start_pos && W->col_start_neg && W->row_index_pos && W->row_index_neg;
+    if (ok) ok = tsg_tcsc_download(dev, W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg) == TSG_OK;
+    if (ok) {
+        pthread_mutex_lock(&g_tab_mu);
+        ok = table_insert(W, dev) == TSG_OK;
+        pthread_mutex_unlock(&g_tab_mu);
+    }
+    if (!ok) { /* tcsc.c:35-43 */
+        free(W->col_start_pos); free(W->col_start_neg); free(W->row_index_pos); free(W->row_index_neg);
+        free(W);
+        tsg_tcsc_destroy(dev);
+        return NULL;
+    }
+    return W;
+}
+
+void tcsc_free(tcsc_t *W) { /* tcsc.c:167-175 */
+    if (!W) return;
+    tsg_tcsc *dev = table_remove(W);
+    if (dev) tsg_tcsc_destroy(dev);
+    free(W->col_start_pos);
+    free(W->col_start_neg);
+    free(W->row_index_pos);
+    free(W->row_index_neg);
+    free(W);
+}
+
+/* ---- GEMM entry points ------------------------------------------------------------------------------------------ */
+static void run_gemm(const float *X, const tcsc_t *W, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K) {
+    tsg_clear_error();
+    if (!W || M <= 0 || N <= 0) return;
+    tsg_tcsc *dev = mirror_of(W);
+    if (!dev) return; /* reason in sparse_last_error() */
+    const int x_dev = tsg_shim_is_device(X), y_dev = tsg_shim_is_device(Y);
+    if (!x_dev && !y_dev) { /* the reference's calling convention: everything in host memory */
+        tsg_shim_tcsc_gemm_hostpipe(dev, X, B, a, use_prelu, order, Y, M, N, K);
+        return;
+    }
+    void *dX = NULL, *dB = NULL, *dY = NULL;
+    int ox = 0, ob = 0, oy = 0;
+    if (tsg_shim_stage_in(X, (size_t)M * K * sizeof(float), &dX, &ox) != TSG_OK) return;
+    if (tsg_shim_stage_in(B, (size_t)N * sizeof(float), &dB, &ob) != TSG_OK) { tsg_shim_release(dX, ox); return; }
+    if (tsg_shim_stage_out_begin(Y, (size_t)M * N * sizeof(float), &dY, &oy) != TSG_OK) {
+        tsg_shim_release(dX, ox); tsg_shim_release(dB, ob);
+        return;
+    }
+    if (tsg_tcsc_gemm(dev, (const float *)dX, (const float *)dB, a, use_prelu, order, (float *)dY, M, N, K, N) == TSG_OK)
+        tsg_shim_stage_out_end(Y, (size_t)M * N * sizeof(float), dY, oy);
+    else
+        tsg_shim_release(dY, oy);
+    tsg_shim_release(dX, ox);
+    tsg_shim_release(dB, ob);
+}
+
+void tcsc_sgemm_basic(const dense_t X, const tcsc_t *W, const dense_t B, dense_t Y, int M, int N, int K) {
+    run_gemm(X, W, B, 0.0f, 0, TSG_ORDER_BIAS_FIRST, Y, M, N, K);
+}
+void tcsc_sgemm_optimized(const dense_t X, const tcsc_t *W, const dense_t B, dense_t Y, int M, int N, int K) {
+    run_gemm(X, W, B, 0.0f, 0, TSG_ORDER_SPLIT, Y, M, N, K);
+}
+void tcsc_sgemm_prelu_basic(const dense_t X, const tcsc_t *W, const dense_t B, float a, dense_t Y, int M, int N, int K) {
+    run_gemm(X, W, B, a, 1, TSG_ORDER_BIAS_LAST, Y, M, N, K);
+}
+void tcsc_sgemm_prelu_optimized_separate(const dense_t X, const tcsc_t *W, const dense_t B, float a, dense_t Y, int M, int N, int K) {
+    run_gemm(X, W, B, a, 1, TSG_ORDER_SPLIT, Y, M, N, K);
+}
+void tcsc_sgemm_prelu_optimized_onthego(const dense_t X, const tcsc_t *W, const dense_t B, float a, dense_t Y, int M, int N, int K) {
+    run_gemm(X, W, B, a, 1, TSG_ORDER_SPLIT, Y, M, N, K);
+}

@@ -1,0 +1,251 @@
+// dist.cu -- column-partitioned multi-GPU path, one process per GPU (BASELINE.json north_star (3)).
+//
+// W's N columns are split across the ranks (output columns are independent: column n needs col_start_*[n..n+1], its
+// index ranges, b[n] and all of X -- tcsc.c:148-163); X is broadcast, each rank computes its M x (N/P) slab, and the
+// slabs are all-gathered so every rank ends with the full Y.  Two realisations of the exchange:
+//   mode 0  NCCL:  ncclBroadcast(X); the kernel writes a contiguous slab; ncclAllGather of the slabs; a re-layout
+//                  kernel interleaves them into row-major Y.
+//   mode 1  fused: Y lives in a symmetric cudaMalloc buffer whose CUDA-IPC mappings of all peers are known to the
+//                  kernel; the GEMM epilogue stores each finished row segment into the local Y and straight into
+//                  every peer's Y over NVLink (P2P stores), so the all-gather overlaps the gather-add tile by tile and
+//                  the extra Y round trip of mode 0 disappears.  A 4-byte ncclAllReduce after the kernel is the
+//                  cross-rank completion barrier.
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded, else the system one), so the
+// library has no link-time NCCL dependency and loads on machines without it.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "tsg_internal.h"
+
+namespace tsg {
+
+// ---- minimal NCCL binding (stable C ABI of NCCL 2.x) -----------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt32 = 2, ncclFloat32 = 7, ncclSum = 0 };
+
+struct Nccl {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+};
+static Nccl g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.lib) return TSG_OK;
+    const char *cands[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void *h = nullptr;
+    for (const char *c : cands)
+        if ((h = dlopen(c, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return set_error(TSG_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define TSG_SYM(field, name)                                                            \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                          \
+    if (!g_nccl.field) return set_error(TSG_ENCCL, "libnccl lacks %s", name);
+    TSG_SYM(GetUniqueId, "ncclGetUniqueId")
+    TSG_SYM(CommInitRank, "ncclCommInitRank")
+    TSG_SYM(CommDestroy, "ncclCommDestroy")
+    TSG_SYM(Broadcast, "ncclBroadcast")
+    TSG_SYM(AllGather, "ncclAllGather")
+    TSG_SYM(AllReduce, "ncclAllReduce")
+    TSG_SYM(GetErrorString, "ncclGetErrorString")
+#undef TSG_SYM
+    g_nccl.lib = h;
+    return TSG_OK;
+}
+
+#define TSG_NCCL(call)                                                                                              \
+    do {                                                                                                            \
+        ncclResult_t r__ = (call);                                                                                  \
+        if (r__ != 0) return set_error(TSG_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));              \
+    } while (0)
+
+// slabs [P][M][wmax] -> Y[M][N] (rank p's columns start at col0(p)); one thread per float4 where possible
+__global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict__ Y, int M, int N, int world, int wmax, int base, int rem) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)M * N) return;
+    const int m = (int)(e / N), n = (int)(e % N);
+    // columns are dealt in units of `base` (+1 unit of 32 for the first `rem` ranks): invert tsg_dist_partition
+    int p, c0;
+    const int big = base + 32;
+    if (n < rem * big) { p = n / big; c0 = p * big; }
+    else { p = rem + (base > 0 ? (n - rem * big) / base : 0); c0 = rem * big + (p - rem) * base; }
+    if (p >= world) { p = world - 1; c0 = rem * big + (p - rem) * base; }
+    Y[e] = G[((size_t)p * M + m) * wmax + (n - c0)];
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+struct tsg_dist {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    // fused mode: symmetric Y buffer + peer mappings
+    float *y_local = nullptr;
+    size_t y_bytes = 0;
+    float *y_peer[TSG_MAX_PEERS] = {nullptr};
+    int *flag = nullptr;
+};
+
+extern "C" {
+
+void tsg_dist_partition(int N, int rank, int world, int *col0, int *ncols) {
+    // deal columns in granules of 32 (kernel tiles and 16-byte alignment); the last rank takes the ragged remainder
+    const int units = N / 32;
+    const int base_u = units / world, rem = units % world;
+    const int base = base_u * 32, big = base + 32;
+    int c0 = (rank < rem) ? rank * big : rem * big + (rank - rem) * base;
+    int nc = (rank < rem) ? big : base;
+    if (rank == world - 1) nc = N - c0;
+    *col0 = c0;
+    *ncols = nc;
+}
+
+int tsg_dist_unique_id(unsigned char id128[128]) {
+    TSG_TRY(load_nccl());
+    ncclUniqueId id;
+    TSG_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return TSG_OK;
+}
+
+int tsg_dist_create(const unsigned char id128[128], int rank, int world, tsg_dist **out) {
+    *out = nullptr;
+    TSG_TRY(ensure_device());
+    TSG_TRY(load_nccl());
+    if (world < 1 || world > TSG_MAX_PEERS || rank < 0 || rank >= world) return set_error(TSG_EINVAL, "tsg_dist_create: bad rank/world");
+    tsg_dist *D = new (std::nothrow) tsg_dist();
+    if (!D) return set_error(TSG_ENOMEM, "out of host memory");
+    D->rank = rank;
+    D->world = world;
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&D->comm, world, id, rank);
+    if (r != 0) {
+        delete D;
+        return set_error(TSG_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    if (cudaMalloc(&D->flag, 16) != cudaSuccess) {
+        g_nccl.CommDestroy(D->comm);
+        delete D;
+        return set_error(TSG_ENOMEM, "cudaMalloc failed");
+    }
+    cudaMemset(D->flag, 0, 16);
+    *out = D;
+    return TSG_OK;
+}
+
+static void dist_unmap(tsg_dist *D) {
+    for (int p = 0; p < D->world; ++p)
+        if (p != D->rank && D->y_peer[p]) cudaIpcCloseMemHandle(D->y_peer[p]);
+    memset(D->y_peer, 0, sizeof D->y_peer);
+    if (D->y_local) cudaFree(D->y_local);
+    D->y_local = nullptr;
+    D->y_bytes = 0;
+}
+
+void tsg_dist_destroy(tsg_dist *D) {
+    if (!D) return;
+    cudaDeviceSynchronize();
+    dist_unmap(D);
+    if (D->flag) cudaFree(D->flag);
+    if (D->comm) g_nccl.CommDestroy(D->comm);
+    delete D;
+}
+
+// Symmetric Y buffer for the fused mode: every rank allocates `bytes` with cudaMalloc and maps all peers' buffers
+// through CUDA IPC (handles exchanged with ncclAllGather).  Collective.  Returns this rank's buffer.
+int tsg_dist_alloc_y(tsg_dist *D, size_t bytes, float **y_local) {
+    *y_local = nullptr;
+    if (!D) return set_error(TSG_EINVAL, "null handle");
+    cudaStream_t st = stream();
+    TSG_CUDA(cudaStreamSynchronize(st));
+    dist_unmap(D);
+    TSG_CUDA(cudaMalloc(&D->y_local, bytes));
+    D->y_bytes = bytes;
+    D->y_peer[D->rank] = D->y_local;
+    if (D->world > 1) {
+        cudaIpcMemHandle_t mine;
+        TSG_CUDA(cudaIpcGetMemHandle(&mine, D->y_local));
+        cudaIpcMemHandle_t *all_d = nullptr;
+        TSG_CUDA(cudaMalloc(&all_d, sizeof(cudaIpcMemHandle_t) * D->world));
+        TSG_CUDA(cudaMemcpy(all_d + D->rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+        TSG_NCCL(g_nccl.AllGather(all_d + D->rank, all_d, sizeof mine, /*ncclChar*/ 0, D->comm, st));
+        TSG_CUDA(cudaStreamSynchronize(st));
+        cudaIpcMemHandle_t all_h[TSG_MAX_PEERS];
+        TSG_CUDA(cudaMemcpy(all_h, all_d, sizeof(cudaIpcMemHandle_t) * D->world, cudaMemcpyDeviceToHost));
+        cudaFree(all_d);
+        for (int p = 0; p < D->world; ++p) {
+            if (p == D->rank) continue;
+            void *ptr = nullptr;
+            TSG_CUDA(cudaIpcOpenMemHandle(&ptr, all_h[p], cudaIpcMemLazyEnablePeerAccess));
+            D->y_peer[p] = static_cast<float *>(ptr);
+        }
+    }
+    *y_local = D->y_local;
+    return TSG_OK;
+}
+
+int tsg_dist_barrier(tsg_dist *D) {
+    if (!D) return set_error(TSG_EINVAL, "null handle");
+    if (D->world > 1) TSG_NCCL(g_nccl.AllReduce(D->flag, D->flag + 1, 1, ncclInt32, ncclSum, D->comm, stream()));
+    return TSG_OK;
+}
+
+int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const float *B, float a, int use_prelu, int order, float *Y, int M,
+                  int N, int K, int mode) {
+    if (!D || !W_local) return set_error(TSG_EINVAL, "tsg_dist_gemm: null handle");
+    TSG_TRY(ensure_device());
+    cudaStream_t st = stream();
+    int col0, ncols;
+    tsg_dist_partition(N, D->rank, D->world, &col0, &ncols);
+    if (W_local->cols != ncols || W_local->rows != K)
+        return set_error(TSG_EINVAL, "tsg_dist_gemm: rank %d owns columns [%d,%d) but W_local is %d x %d", D->rank, col0, col0 + ncols,
+                         W_local->rows, W_local->cols);
+    // (1) X broadcast
+    if (root >= 0 && D->world > 1) TSG_NCCL(g_nccl.Broadcast(X, X, (size_t)M * K, ncclFloat32, root, D->comm, st));
+    if (D->world == 1) return tsg_tcsc_gemm(W_local, X, B, a, use_prelu, order, Y, M, N, K, N);
+
+    if (mode == 1) {
+        // (2+3 fused) kernel stores into the local Y and every peer's Y
+        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 1): Y must be the buffer returned by tsg_dist_alloc_y");
+        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 1): Y buffer too small");
+        float *peers[TSG_MAX_PEERS];
+        int np = 0;
+        for (int p = 1; p < D->world; ++p) {  // start with the next rank so that the ranks do not all hit the same peer first
+            const int q = (D->rank + p) % D->world;
+            peers[np++] = D->y_peer[q] + col0;
+        }
+        // every rank must have finished READING its previous Y before a peer overwrites it
+        TSG_TRY(tsg_dist_barrier(D));
+        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers));
+        return tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
+    }
+
+    // mode 0: (2) contiguous slab, (3) ncclAllGather + re-layout
+    int c0_0, w0;
+    tsg_dist_partition(N, 0, D->world, &c0_0, &w0);
+    int wl, cl;
+    tsg_dist_partition(N, D->world - 1, D->world, &cl, &wl);
+    const int wmax = (w0 > wl) ? w0 : wl;
+    float *G = nullptr;
+    TSG_TRY(dev_alloc_t(&G, (size_t)D->world * M * wmax));
+    float *slab = G + (size_t)D->rank * M * wmax;
+    if (ncols > 0) TSG_TRY(tsg_tcsc_gemm(W_local, X, B + col0, a, use_prelu, order, slab, M, ncols, K, wmax));
+    TSG_NCCL(g_nccl.AllGather(slab, G, (size_t)M * wmax, ncclFloat32, D->comm, st));
+    const int units = N / 32, base = (units / D->world) * 32, rem = units % D->world;
+    const long long total = (long long)M * N;
+    k_relayout_slabs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(G, Y, M, N, D->world, wmax, base, rem);
+    TSG_KERNEL_CHECK("k_relayout_slabs");
+    return dev_free(G);
+}
+
+}  // extern "C"

@@ -1,0 +1,474 @@
+// gemm_tcsc.cu -- the multiplication-free sparse ternary GEMM  Y = [PReLU](X*W + B)  on sm_100a.
+//
+// Replaces tcsc_sgemm_basic / _optimized / _prelu_basic / _prelu_optimized_separate / _prelu_optimized_onthego
+// (sparse/tcsc.c:69-165,179-275) and sparseGEMM<float> / sparseGEMM_PReLU<float> (SparseGEMM.h:104-119,151-168).
+//
+// Tiled kernel (M >= TSG_SKINNY_M).  One persistent CTA per SM walks work units (128 rows of X) x (TN columns of W):
+//   * lanes own rows: lane l of every warp holds rows 4l..4l+3 of the 128-row tile, a warp owns CW columns, so each
+//     thread keeps CW x 4 accumulators in registers and the k index of every non-zero is warp-uniform;
+//   * X is pre-transposed once per call into K-major 128-row tiles XT[mtile][k][128] (transpose_x_tiles), so that a
+//     kc-row chunk of a tile is ONE contiguous block: a producer thread streams chunk after chunk into a two-stage
+//     shared-memory ring with bulk async copies (cp.async.bulk, TMA engine) completing on mbarriers, together with
+//     the tile's slice of the private gather stream (ktformat.cu);
+//   * per non-zero a warp issues one conflict-free LDS.128 (32 lanes x 16 B = the tile's row k) and four FADDs per
+//     lane -- no multiplies, no tensor cores.  The binding resource is the shared-memory crossbar (128 B/clk/SM =
+//     one warp-wide add per clock per SM = 25 % of the FP32 add peak; profiles/microbench/);
+//   * bias, PReLU and the store of Y are fused into the epilogue; Y may be a column slab of a wider matrix (ldy).
+// Summation order: a unit makes two sweeps over the K chunks, first the +1 entries, then the -1 entries, each in
+// ascending k, with a single accumulator per output -- the exact sequence of fp32 roundings of the reference
+// function selected by `order` (DESIGN.md "Summation order").
+//
+// Skinny kernel (M < TSG_SKINNY_M, the decode shape): HBM/L2-bound on the index stream.  One warp per column, lanes
+// stride over the column's non-zeros (coalesced index loads), gather up to 8 rows of X per index from a K-major copy
+// of X, tree-reduce across the warp.
+#include "tsg_internal.h"
+
+namespace tsg {
+
+constexpr int TM = 128;     // rows of X per tile
+constexpr int NWARP = 16;   // compute warps per CTA
+constexpr int NTHREADS = (NWARP + 4) * 32;  // 4 compute warpgroups + 1 producer warpgroup (register re-balancing is per warpgroup)
+constexpr int REGS_COMPUTE = 120, REGS_PRODUCER = 24;
+constexpr int WOFF_BYTES = 160;  // (256/8 + 1) offsets, rounded up to 16 B
+constexpr int CNT_BYTES = 256;
+
+struct GemmParams {
+    const float *XT;
+    const uint8_t *cnt;
+    const uint32_t *woff;
+    const uint32_t *body;
+    const float *B;
+    float *Y;
+    long long ldy;
+    int M, N, K;
+    int kc, nchunk, ncols_pad, ngroup;
+    int mtiles, ntiles;
+    float a;
+    int use_prelu, order;
+    uint32_t xstage_bytes, body_stage_bytes;
+    // column-partitioned multi-GPU path: the epilogue additionally stores the finished slab into every peer's Y
+    // (NVLink peer mappings, already offset to this rank's first column); 0 = single GPU
+    int npeer;
+    float *peerY[TSG_MAX_PEERS];
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---- gather-add over one chunk for the CW columns of a warp ------------------------------------------------------------
+template <int CW, bool NEG>
+__device__ __forceinline__ void gather_chunk(float (&acc)[CW][4], const float *__restrict__ xs, const uint8_t *__restrict__ cnt_s,
+                                             const uint32_t *__restrict__ woff_s, const uint32_t *__restrict__ body_s, int warp, int lane) {
+    // word offset of this warp's first column inside the staged body slice
+    const int col0 = warp * CW;
+    uint32_t off = woff_s[col0 >> 3] - woff_s[0];
+    if (CW < 8) {
+        for (int i = 0; i < (col0 & 7); ++i) off += cnt_s[(col0 & ~7) + i];
+    }
+    uint32_t cw[(CW + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (CW + 3) / 4; ++i) cw[i] = *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i);
+    const uint32_t *wp = body_s + off;
+    const float *xl = xs + lane * 4;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        const int nw = (cw[j >> 2] >> (8 * (j & 3))) & 0xFF;
+        for (int i = 0; i < nw; ++i) {
+            const uint32_t word = *wp++;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t k = (word >> (8 * e)) & 0xFFu;
+                if (k != 0xFFu) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xl + k * TM);
+                    if (NEG) {
+                        acc[j][0] -= x.x; acc[j][1] -= x.y; acc[j][2] -= x.z; acc[j][3] -= x.w;
+                    } else {
+                        acc[j][0] += x.x; acc[j][1] += x.y; acc[j][2] += x.z; acc[j][3] += x.w;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int TN = CW * NWARP;
+    const uint32_t stage_bytes = p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)stage_bytes);
+    uint64_t *empty = full + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], NWARP);
+        mbar_init(&empty[1], NWARP);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int units = p.mtiles * p.ntiles;
+
+    if (warp >= NWARP) {
+        // ===== producer warpgroup: hands its registers to the compute warpgroups; one thread feeds the two-stage ring =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        if (warp == NWARP && lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int mt = u / p.ntiles, nt = u % p.ntiles;
+                const int n0 = nt * TN;
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int c = 0; c < p.nchunk; ++c, ++it) {
+                        const uint32_t s = it & 1u;
+                        mbar_wait(&empty[s], ((it >> 1) & 1u) ^ 1u);
+                        uint8_t *st = smem + (size_t)s * stage_bytes;
+                        const int plane = pass * p.nchunk + c;
+                        const int rows = min(p.kc, p.K - c * p.kc);
+                        const uint32_t xbytes = (uint32_t)rows * (TM * 4);
+                        const size_t gidx = (size_t)plane * p.ngroup + (n0 >> 3);
+                        const uint32_t w0 = __ldg(p.woff + gidx), w1 = __ldg(p.woff + gidx + TN / 8);
+                        const uint32_t bbytes = (w1 - w0) * 4u;
+                        constexpr uint32_t woff_copy = (((TN / 8 + 1) * 4) + 15) & ~15;
+                        mbar_arrive_expect_tx(&full[s], xbytes + bbytes + TN + woff_copy);
+                        bulk_g2s(st, p.XT + ((size_t)mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
+                        if (bbytes) bulk_g2s(st + p.xstage_bytes, p.body + w0, bbytes, &full[s]);
+                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + n0, TN, &full[s]);
+                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes + CNT_BYTES, p.woff + gidx, woff_copy, &full[s]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: 16 warps x CW columns, 4 rows per lane =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+    float acc[CW][4];
+    uint32_t it = 0;
+    const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int mt = u / p.ntiles, nt = u % p.ntiles;
+        const int nbase = nt * TN + warp * CW;
+        const int mbase = mt * TM + lane * 4;
+        // the bias is re-read (L1/L2 hit) where it is needed instead of living in CW registers across the gather loops
+        auto bias_of = [&](int j) { return (nbase + j < p.N) ? __ldg(p.B + nbase + j) : 0.f; };
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const float init = (p.order == TSG_ORDER_BIAS_FIRST) ? bias_of(j) : 0.f;  // tcsc.c:84 vs tcsc.c:149
+            acc[j][0] = init; acc[j][1] = init; acc[j][2] = init; acc[j][3] = init;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && p.order == TSG_ORDER_SPLIT) {
+                // tcsc.c:125,138: Y = B + acc_pos is rounded and parked in Y, acc_neg starts from 0
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int m = mbase + v;
+                    if (m < p.M) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j)
+                            if (nbase + j < p.N) p.Y[(size_t)m * p.ldy + nbase + j] = bias_of(j) + acc[j][v];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+            }
+            const bool neg = (pass == 1) && (p.order != TSG_ORDER_SPLIT);
+            for (int c = 0; c < p.nchunk; ++c, ++it) {
+                const uint32_t s = it & 1u;
+                mbar_wait(&full[s], (it >> 1) & 1u);
+                const uint8_t *st = smem + (size_t)s * stage_bytes;
+                const float *xs = reinterpret_cast<const float *>(st);
+                const uint32_t *body_s = reinterpret_cast<const uint32_t *>(st + p.xstage_bytes);
+                const uint8_t *cnt_s = st + p.xstage_bytes + p.body_stage_bytes;
+                const uint32_t *woff_s = reinterpret_cast<const uint32_t *>(cnt_s + CNT_BYTES);
+                if (neg) gather_chunk<CW, true>(acc, xs, cnt_s, woff_s, body_s, warp, lane);
+                else gather_chunk<CW, false>(acc, xs, cnt_s, woff_s, body_s, warp, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+        }
+        // ---- fused epilogue: bias, PReLU, store ----
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int m = mbase + v;
+            if (m >= p.M) continue;
+            float *yrow = p.Y + (size_t)m * p.ldy + nbase;
+            float out[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                float y;
+                if (p.order == TSG_ORDER_BIAS_FIRST) y = acc[j][v];
+                else if (p.order == TSG_ORDER_BIAS_LAST) y = acc[j][v] + bias_of(j);                       // tcsc.c:161
+                else y = ((nbase + j < p.N) ? yrow[j] : 0.f) - acc[j][v];                               // tcsc.c:138
+                if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;                                          // tcsc.c:162
+                out[j] = y;
+            }
+            if (vec_ok && CW % 4 == 0 && nbase + CW <= p.N) {
+#pragma unroll
+                for (int j = 0; j < CW; j += 4)
+                    *reinterpret_cast<float4 *>(yrow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                // fused all-gather: the same 64-byte row segment goes to every peer over NVLink (peer pointers share
+                // the local Y's alignment and pitch)
+                for (int q = 0; q < p.npeer; ++q) {
+                    float *prow = p.peerY[q] + (size_t)m * p.ldy + nbase;
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4)
+                        *reinterpret_cast<float4 *>(prow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j)
+                    if (nbase + j < p.N) yrow[j] = out[j];
+                for (int q = 0; q < p.npeer; ++q) {
+                    float *prow = p.peerY[q] + (size_t)m * p.ldy + nbase;
+#pragma unroll
+                    for (int j = 0; j < CW; ++j)
+                        if (nbase + j < p.N) prow[j] = out[j];
+                }
+            }
+        }
+    }
+}
+
+// ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transpose_x(const float *__restrict__ X, float *__restrict__ XT, int M, int K) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 8 * i, k = k0 + tx;
+        tile[ty + 8 * i][tx] = (m < M && k < K) ? __ldg(X + (size_t)m * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty + 8 * i, m = m0 + tx;
+        if (k < K) {
+            const int mt = m / TM, ml = m % TM;
+            XT[((size_t)mt * K + k) * TM + ml] = tile[tx][ty + 8 * i];
+        }
+    }
+}
+
+int transpose_x_tiles(const float *X, float *XT, int M, int K) {
+    const int mtiles = (M + TM - 1) / TM;
+    dim3 grid((K + 31) / 32, mtiles * (TM / 32));
+    k_transpose_x<<<grid, 256, 0, stream()>>>(X, XT, M, K);
+    TSG_KERNEL_CHECK("k_transpose_x");
+    return TSG_OK;
+}
+
+// =====================================================================================================================
+// skinny kernel
+// =====================================================================================================================
+constexpr int SK_MT = 8;  // rows of X handled together
+
+// X rows [m0, m0+8) -> XS[group][k][8] (zero padded)
+__global__ void k_skinny_pack_x(const float *__restrict__ X, float *__restrict__ XS, int M, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (k >= K) return;
+    float v[SK_MT];
+#pragma unroll
+    for (int i = 0; i < SK_MT; ++i) {
+        const int m = g * SK_MT + i;
+        v[i] = (m < M) ? __ldg(X + (size_t)m * K + k) : 0.f;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(XS + ((size_t)g * K + k) * SK_MT);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <int MT>
+__device__ __forceinline__ void skinny_accumulate(float (&acc)[MT], const float *__restrict__ xs, const int *__restrict__ idx, int lo,
+                                                  int hi, int lane, float sign) {
+    for (int t = lo + lane; t < hi; t += 32) {
+        const int k = __ldg(idx + t);
+        const float *px = xs + (size_t)k * SK_MT;
+        if (MT <= 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(px));
+            acc[0] += sign * a.x;
+            if (MT > 1) acc[1 % MT] += sign * a.y;
+            if (MT > 2) { acc[2 % MT] += sign * a.z; acc[3 % MT] += sign * a.w; }
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(px));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(px) + 1);
+            acc[0] += sign * a.x; acc[1 % MT] += sign * a.y; acc[2 % MT] += sign * a.z; acc[3 % MT] += sign * a.w;
+            acc[4 % MT] += sign * b.x; acc[5 % MT] += sign * b.y; acc[6 % MT] += sign * b.z; acc[7 % MT] += sign * b.w;
+        }
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) k_tcsc_skinny(const float *__restrict__ XS, const int *__restrict__ csp, const int *__restrict__ csn,
+                                                     const int *__restrict__ rip, const int *__restrict__ rin, const float *__restrict__ B,
+                                                     float a, int use_prelu, float *__restrict__ Y, long long ldy, int M, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int g = blockIdx.y;
+    const float *xs = XS + (size_t)g * K * SK_MT;
+    for (int n = wglobal; n < N; n += nwarps) {
+        float acc[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) acc[i] = 0.f;
+        skinny_accumulate<MT>(acc, xs, rip, __ldg(csp + n), __ldg(csp + n + 1), lane, 1.0f);
+        skinny_accumulate<MT>(acc, xs, rin, __ldg(csn + n), __ldg(csn + n + 1), lane, -1.0f);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
+        }
+        if (lane == 0) {
+            const float b = __ldg(B + n);
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int m = g * SK_MT + i;
+                if (m < M) {
+                    float y = acc[i] + b;
+                    if (use_prelu) y = (y < 0.0f) ? a * y : y;
+                    Y[(size_t)m * ldy + n] = y;
+                }
+            }
+        }
+    }
+}
+
+static thread_local int g_force_kernel = 0;
+
+static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy) {
+    cudaStream_t st = stream();
+    const int groups = (M + SK_MT - 1) / SK_MT;
+    float *XS = nullptr;
+    TSG_TRY(dev_alloc_t(&XS, (size_t)groups * K * SK_MT));
+    k_skinny_pack_x<<<dim3((K + 255) / 256, groups), 256, 0, st>>>(X, XS, M, K);
+    TSG_KERNEL_CHECK("k_skinny_pack_x");
+    const int warps_per_cta = 8;
+    int ctas = (N + warps_per_cta - 1) / warps_per_cta;
+    const int max_ctas = num_sms() * 8;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    dim3 grid(ctas, groups);
+    const int mt = (M >= 5) ? 8 : (M >= 3 ? 4 : (M == 2 ? 2 : 1));
+    switch (mt) {
+        case 1: k_tcsc_skinny<1><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        case 2: k_tcsc_skinny<2><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        case 4: k_tcsc_skinny<4><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        default: k_tcsc_skinny<8><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+    }
+    TSG_KERNEL_CHECK("k_tcsc_skinny");
+    return dev_free(XS);
+}
+
+template <int CW>
+static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    const int units = p.mtiles * p.ntiles;
+    const int grid = units < num_sms() ? units : num_sms();
+    k_tcsc_gemm<CW><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    TSG_KERNEL_CHECK("k_tcsc_gemm");
+    return TSG_OK;
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+namespace tsg {
+int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
+                    long long ldy, int npeer, float *const *peerY);
+}
+
+extern "C" {
+
+int tsg_tcsc_set_kernel(int which) {
+    g_force_kernel = which;
+    return TSG_OK;
+}
+
+int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
+                  long long ldy) {
+    return tcsc_gemm_peers(W, X, B, a, use_prelu, order, Y, M, N, K, ldy, 0, nullptr);
+}
+
+}  // extern "C"
+
+namespace tsg {
+int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
+                    long long ldy, int npeer, float *const *peerY) {
+    TSG_TRY(ensure_device());
+    if (npeer < 0 || npeer > TSG_MAX_PEERS) return set_error(TSG_EINVAL, "too many peers");
+    if (!W || !X || !B || !Y) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: null argument");
+    if (N != W->cols || K != W->rows) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: W is %d x %d but K=%d, N=%d", W->rows, W->cols, K, N);
+    if (order < 0 || order > 2) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
+    if (ldy < N) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: ldy < N");
+    if (M <= 0 || N <= 0) return TSG_OK;
+    const bool skinny = npeer == 0 && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
+    if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
+
+    TSG_TRY(build_kstream(W));
+    const KStream &ks = W->ks;
+    GemmParams p;
+    p.mtiles = (M + TM - 1) / TM;
+    float *XT = nullptr;
+    TSG_TRY(dev_alloc_t(&XT, (size_t)p.mtiles * (K > 0 ? K : 1) * TM));
+    if (K > 0) TSG_TRY(transpose_x_tiles(X, XT, M, K));
+    p.XT = XT; p.cnt = ks.cnt; p.woff = ks.woff; p.body = ks.body; p.B = B; p.Y = Y; p.ldy = ldy;
+    p.M = M; p.N = N; p.K = K; p.kc = ks.kc; p.nchunk = (K > 0) ? ks.nchunk : 0; p.ncols_pad = ks.ncols_pad; p.ngroup = ks.ngroup;
+    p.a = a; p.use_prelu = use_prelu; p.order = order;
+    p.npeer = npeer;
+    for (int q = 0; q < TSG_MAX_PEERS; ++q) p.peerY[q] = (q < npeer) ? peerY[q] : nullptr;
+    p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
+    p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
+    const size_t smem_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES) + 64;
+    // column tile: 256 (CW=16) when that still gives every SM a few units, else narrower tiles for more parallelism
+    const int sms = num_sms();
+    int rc;
+    auto units_for = [&](int cw) { return p.mtiles * ((N + 16 * cw - 1) / (16 * cw)); };
+    if (units_for(16) >= 2 * sms || units_for(8) <= units_for(16)) {
+        p.ntiles = (N + 255) / 256;
+        rc = launch_tiled<16>(p, smem_bytes);
+    } else if (units_for(8) >= sms || units_for(4) <= units_for(8)) {
+        p.ntiles = (N + 127) / 128;
+        rc = launch_tiled<8>(p, smem_bytes);
+    } else {
+        p.ntiles = (N + 63) / 64;
+        rc = launch_tiled<4>(p, smem_bytes);
+    }
+    int rc2 = dev_free(XT);
+    return rc ? rc : rc2;
+}
+}  // namespace tsg

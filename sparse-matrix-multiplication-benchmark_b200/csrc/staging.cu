@@ -1,0 +1,118 @@
+// staging.cu -- host<->device staging for the reference-named entry points (callers hand us host buffers).
+#include "tsg_host_shim.h"
+#include "tsg_internal.h"
+
+using namespace tsg;
+
+extern "C" {
+
+int tsg_shim_is_device(const void *p) { return is_device_pointer(p); }
+
+int tsg_shim_stage_in(const void *p, size_t bytes, void **dev, int *owned) {
+    TSG_TRY(ensure_device());
+    if (is_device_pointer(p)) {
+        *dev = const_cast<void *>(p);
+        *owned = 0;
+        return TSG_OK;
+    }
+    TSG_TRY(dev_alloc(dev, bytes));
+    *owned = 1;
+    if (bytes) TSG_CUDA(cudaMemcpyAsync(*dev, p, bytes, cudaMemcpyHostToDevice, stream()));
+    return TSG_OK;
+}
+
+int tsg_shim_stage_out_begin(void *p, size_t bytes, void **dev, int *owned) {
+    TSG_TRY(ensure_device());
+    if (is_device_pointer(p)) {
+        *dev = p;
+        *owned = 0;
+        return TSG_OK;
+    }
+    *owned = 1;
+    return dev_alloc(dev, bytes);
+}
+
+int tsg_shim_stage_out_end(void *p, size_t bytes, void *dev, int owned) {
+    if (!owned) return TSG_OK;
+    if (bytes) TSG_CUDA(cudaMemcpyAsync(p, dev, bytes, cudaMemcpyDeviceToHost, stream()));
+    TSG_CUDA(cudaStreamSynchronize(stream()));
+    return dev_free(dev);
+}
+
+int tsg_shim_release(void *dev, int owned) { return owned ? dev_free(dev) : TSG_OK; }
+
+// ---- pipelined host-pointer GEMM ----------------------------------------------------------------------------------------
+// X and Y live in host memory (pinned or pageable).  Rows are independent, so the call is cut into row slabs and the
+// three legs -- H2D of slab i+1, kernel on slab i, D2H of slab i-1 -- run concurrently on three streams; PCIe is full
+// duplex, so the wall time approaches max(H2D, D2H) + one slab instead of H2D + kernel + D2H.
+int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any, float a, int use_prelu, int order, float *Y, int M,
+                                int N, int K) {
+    TSG_TRY(ensure_device());
+    cudaStream_t user = stream();
+    static thread_local cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    if (!s_in) {
+        TSG_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        TSG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        TSG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    }
+    TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
+    // slab: a multiple of 128 rows giving every SM a few work units; at least 4 slabs when M allows
+    int slab = 1024;
+    while (slab > 128 && (M + slab - 1) / slab < 4) slab >>= 1;
+    if (M < TSG_SKINNY_M) slab = M;
+    const int nslab = (M + slab - 1) / slab;
+    const int nbuf = nslab < 3 ? nslab : 3;
+    float *dX[3] = {nullptr, nullptr, nullptr}, *dY[3] = {nullptr, nullptr, nullptr}, *dB = nullptr;
+    cudaEvent_t ev_in[3], ev_k[3], ev_out[3];
+    int rc = TSG_OK;
+    tsg_set_stream(s_k);
+    int b_owned = 0;
+    void *bdev = nullptr;
+    if ((rc = tsg_shim_stage_in(B_any, (size_t)N * 4, &bdev, &b_owned))) { tsg_set_stream(user); return rc; }
+    dB = static_cast<float *>(bdev);
+    for (int i = 0; i < nbuf && !rc; ++i) {
+        rc = dev_alloc_t(&dX[i], (size_t)slab * K);
+        if (!rc) rc = dev_alloc_t(&dY[i], (size_t)slab * N);
+        cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+    }
+    if (!rc) rc = build_kstream(W);  // on s_k
+    cudaStreamSynchronize(s_k);      // pool allocations above are ordered on s_k; the copy streams use them next
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nslab && !rc && e == cudaSuccess; ++i) {
+        const int b = i % nbuf;
+        const int m0 = i * slab, rows = (M - m0 < slab) ? (M - m0) : slab;
+        if (i >= nbuf) {  // buffer reuse: the kernel that read dX[b] and the copy that drained dY[b] must be done
+            e = cudaStreamWaitEvent(s_in, ev_k[b], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, ev_out[b], 0);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dX[b], X + (size_t)m0 * K, (size_t)rows * K * 4, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[b], s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, ev_in[b], 0);
+        if (e != cudaSuccess) break;
+        rc = tsg_tcsc_gemm(W, dX[b], dB, a, use_prelu, order, dY[b], rows, N, K, N);
+        if (rc) break;
+        e = cudaEventRecord(ev_k[b], s_k);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev_k[b], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(Y + (size_t)m0 * N, dY[b], (size_t)rows * N * 4, cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_out[b], s_out);
+    }
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_k);
+    cudaError_t e2 = cudaStreamSynchronize(s_out);
+    for (int i = 0; i < nbuf; ++i) {
+        dev_free(dX[i]);
+        dev_free(dY[i]);
+        cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_k[i]); cudaEventDestroy(ev_out[i]);
+    }
+    tsg_shim_release(dB, b_owned);
+    cudaStreamSynchronize(s_k);
+    tsg_set_stream(user);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return set_error(TSG_ECUDA, "pipelined GEMM failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return TSG_OK;
+}
+
+}  // extern "C"

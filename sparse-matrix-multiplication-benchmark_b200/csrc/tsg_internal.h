@@ -1,0 +1,103 @@
+// tsg_internal.h -- declarations shared by the CUDA translation units of libtsgemm_b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+#include "tsgemm_b200.h"
+
+#define TSG_MAX_PEERS 8
+
+namespace tsg {
+
+// ---- error channel (thread-local message, returned by tsg_last_error / sparse_last_error) ------------------------
+int set_error(int code, const char *fmt, ...);
+void clear_error();
+
+#define TSG_CUDA(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return ::tsg::set_error(TSG_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                                    __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define TSG_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != TSG_OK) return rc__; \
+    } while (0)
+
+#define TSG_KERNEL_CHECK(name)                                                                              \
+    do {                                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                               \
+        if (e__ != cudaSuccess)                                                                             \
+            return ::tsg::set_error(TSG_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));   \
+        ::tsg::count_launch();                                                                              \
+    } while (0)
+
+// ---- runtime state ------------------------------------------------------------------------------------------------
+cudaStream_t stream();
+void count_launch();
+int num_sms();
+int ensure_device();  // TSG_OK iff a usable sm_100 device is current (cached)
+
+int dev_alloc(void **out, size_t bytes);
+int dev_free(void *p);
+template <typename T>
+inline int dev_alloc_t(T **out, size_t count) {
+    return dev_alloc(reinterpret_cast<void **>(out), count * sizeof(T));
+}
+
+// ---- private K-tiled gather stream of a TCSC matrix (ktformat.cu) --------------------------------------------------
+// Plane p = sign * nchunk + chunk holds, for every column, the local row numbers (k - chunk*kc, one byte each, four
+// per 32-bit word, 0xFF padding) of that column's +1 (sign 0) / -1 (sign 1) entries that fall into the chunk.
+struct KStream {
+    int kc = 0;           // rows of X per chunk (<= 255)
+    int nchunk = 0;       // ceil(K / kc)
+    int ncols_pad = 0;    // N rounded up to a multiple of 256
+    int ngroup = 0;       // ncols_pad / 8 (offset granule: 8 columns)
+    uint8_t *cnt = nullptr;    // [2*nchunk][ncols_pad]   words per column
+    uint32_t *woff = nullptr;  // [2*nchunk][ngroup + 4]  word offset (into body) of each 8-column group, 4-word aligned
+    uint32_t *body = nullptr;  // packed words
+    long long body_words = 0;  // capacity
+    int max_tile_words = 0;    // max over planes and 256-column tiles of the tile's body words
+    bool built = false;
+};
+
+}  // namespace tsg
+
+// opaque handle of tsgemm_b200.h
+struct tsg_tcsc {
+    int rows = 0, cols = 0, n_pos = 0, n_neg = 0;
+    int *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;  // device
+    tsg::KStream ks;
+};
+
+struct tsg_bcsr {
+    int r = 0, c = 0, br = 0, bc = 0, k = 0;
+    int *row_start = nullptr, *col_idx = nullptr;  // device, reference layout (block-row major)
+    float *values = nullptr;
+    // private column-major mirror (ascending block-row inside each block-column) used by the kernel
+    int *cptr = nullptr;   // [bc+1]
+    int *crow = nullptr;   // [k] block-row of each block in column-major order
+    int *cblk = nullptr;   // [k] index of the block in `values`
+    bool col_built = false;
+};
+
+namespace tsg {
+// exclusive prefix sum over n uint32 (out may not alias in); grand total written to *total_dev (convert.cu)
+int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t *total_dev);
+// classify a pointer: 1 device (or managed), 0 host
+int is_device_pointer(const void *p);
+int build_kstream(tsg_tcsc *W);
+int bcsr_build_cols(tsg_bcsr *W);
+// tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu)
+int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
+                    long long ldy, int npeer, float *const *peerY);
+// X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
+int transpose_x_tiles(const float *X, float *XT, int M, int K);
+}  // namespace tsg
