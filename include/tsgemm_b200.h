@@ -83,6 +83,7 @@ int tsg_tcsc_gemm(tsg_tcsc *W, const float *X_dev, const float *B_dev, float a, 
                   float *Y_dev, int M, int N, int K, long long ldy);
 /* force one kernel: 0 auto, 1 tiled shared-memory gather kernel, 2 skinny kernel */
 int tsg_tcsc_set_kernel(int which);
+int tsg_tcsc_get_kernel(void);
 
 /* ---- BCSR device mirror --------------------------------------------------------------------------------------- */
 typedef struct tsg_bcsr tsg_bcsr;

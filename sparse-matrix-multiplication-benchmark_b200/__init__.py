@@ -49,12 +49,12 @@ def lib() -> C.CDLL:
         return _lib
     if not os.path.exists(LIB_PATH):
         raise TsgError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() -- there is no CPU fallback")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(LIB_PATH)  # RTLD_LOCAL: our reference-named symbols must not interpose on other libraries
     i, f, vp, ll = C.c_int, C.c_float, C.c_void_p, C.c_longlong
     ip = C.POINTER(C.c_int)
     # ---- reference-named entry points
     L.tcsc_from_dense.argtypes, L.tcsc_from_dense.restype = [vp, i, i], C.POINTER(tcsc_t)
-    L.tcsc_free.argtypes = [C.POINTER(tcsc_t)]
+    L.tcsc_free.argtypes, L.tcsc_free.restype = [C.POINTER(tcsc_t)], None
     for n in ("tcsc_sgemm_basic", "tcsc_sgemm_optimized"):
         getattr(L, n).argtypes, getattr(L, n).restype = [vp, C.POINTER(tcsc_t), vp, vp, i, i, i], None
     for n in ("tcsc_sgemm_prelu_basic", "tcsc_sgemm_prelu_optimized_separate", "tcsc_sgemm_prelu_optimized_onthego"):

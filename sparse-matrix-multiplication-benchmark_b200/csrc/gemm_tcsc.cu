@@ -28,7 +28,8 @@ namespace tsg {
 constexpr int TM = 128;     // rows of X per tile
 constexpr int NWARP = 16;   // compute warps per CTA
 constexpr int NTHREADS = (NWARP + 4) * 32;  // 4 compute warpgroups + 1 producer warpgroup (register re-balancing is per warpgroup)
-constexpr int REGS_COMPUTE = 120, REGS_PRODUCER = 24;
+// register re-balancing happens inside the CTA's own pool: 4 x 128 x (112 - 96) <= 128 x (96 - 24), else setmaxnreg.inc never returns
+constexpr int REGS_COMPUTE = 112, REGS_PRODUCER = 24;
 constexpr int WOFF_BYTES = 160;  // (256/8 + 1) offsets, rounded up to 16 B
 constexpr int CNT_BYTES = 256;
 
@@ -42,7 +43,8 @@ struct GemmParams {
     long long ldy;
     int M, N, K;
     int kc, nchunk, ncols_pad, ngroup;
-    int mtiles, ntiles;
+    int mtiles, ntiles;          // ntiles = number of 256-column tiles
+    int units_full, units_total, sub;  // unit decomposition, see decode_unit()
     float a;
     int use_prelu, order;
     uint32_t xstage_bytes, body_stage_bytes;
@@ -81,46 +83,87 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
-// ---- gather-add over one chunk for the CW columns of a warp ------------------------------------------------------------
-template <int CW, bool NEG>
-__device__ __forceinline__ void gather_chunk(float (&acc)[CW][4], const float *__restrict__ xs, const uint8_t *__restrict__ cnt_s,
-                                             const uint32_t *__restrict__ woff_s, const uint32_t *__restrict__ body_s, int warp, int lane) {
-    // word offset of this warp's first column inside the staged body slice
-    const int col0 = warp * CW;
-    uint32_t off = woff_s[col0 >> 3] - woff_s[0];
-    if (CW < 8) {
-        for (int i = 0; i < (col0 & 7); ++i) off += cnt_s[(col0 & ~7) + i];
-    }
-    uint32_t cw[(CW + 3) / 4];
+// ---- gather-add over one chunk for the columns of a warp ---------------------------------------------------------------
+// Accumulators are kept as packed fp32x2 pairs (rows 4l,4l+1 and 4l+2,4l+3 of the tile) so that one FADD2 (add.f32x2,
+// sm_100) retires two adds per issue slot; each component is an ordinary IEEE fp32 add, so the roundings are unchanged.
+// One 32-bit word of the gather stream holds up to four non-zeros; a 0xFF byte is padding: its load and adds are
+// predicated off, so it costs issue slots but no shared-memory bandwidth.  Adds are applied in stream order.
+template <bool NEG>
+__device__ __forceinline__ void gather_word(float2 &a01, float2 &a23, uint32_t word, uint32_t xbase) {
 #pragma unroll
-    for (int i = 0; i < (CW + 3) / 4; ++i) cw[i] = *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i);
-    const uint32_t *wp = body_s + off;
-    const float *xl = xs + lane * 4;
-#pragma unroll
-    for (int j = 0; j < CW; ++j) {
-        const int nw = (cw[j >> 2] >> (8 * (j & 3))) & 0xFF;
-        for (int i = 0; i < nw; ++i) {
-            const uint32_t word = *wp++;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t k = (word >> (8 * e)) & 0xFFu;
-                if (k != 0xFFu) {
-                    const float4 x = *reinterpret_cast<const float4 *>(xl + k * TM);
-                    if (NEG) {
-                        acc[j][0] -= x.x; acc[j][1] -= x.y; acc[j][2] -= x.z; acc[j][3] -= x.w;
-                    } else {
-                        acc[j][0] += x.x; acc[j][1] += x.y; acc[j][2] += x.z; acc[j][3] += x.w;
-                    }
-                }
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t k = (word >> (8 * e)) & 0xFFu;
+        if (k != 0xFFu) {  // warp-uniform: compiles to predicated LDS.128 + FADD2, no branch
+            float4 x;  // 32-bit shared-window address: no generic->shared conversion per load
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(k * (TM * 4) + xbase));
+            if (NEG) {
+                a01 = __fadd2_rn(a01, make_float2(-x.x, -x.y));
+                a23 = __fadd2_rn(a23, make_float2(-x.z, -x.w));
+            } else {
+                a01 = __fadd2_rn(a01, make_float2(x.x, x.y));
+                a23 = __fadd2_rn(a23, make_float2(x.z, x.w));
             }
         }
     }
 }
 
-template <int CW>
+constexpr int CWMAX = 16;  // columns per warp in a full (256-column) tile; tail units use 8 or 4 (runtime `cw`)
+
+template <bool NEG>
+__device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t xbase, const uint8_t *__restrict__ cnt_s,
+                                             const uint32_t *__restrict__ woff_s, const uint32_t *__restrict__ body_s, int warp, int cw) {
+    // word offset of this warp's first column inside the staged body slice
+    const int col0 = warp * cw;
+    uint32_t off = woff_s[col0 >> 3] - woff_s[0];
+    if (col0 & 7) {  // cw == 4: the warp starts in the middle of an 8-column group
+        const uint32_t prev = *reinterpret_cast<const uint32_t *>(cnt_s + (col0 & ~7));
+        off += __vsadu4(prev, 0u);
+    }
+    uint32_t cwd[CWMAX / 4];
+#pragma unroll
+    for (int i = 0; i < CWMAX / 4; ++i) cwd[i] = (4 * i < cw) ? *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i) : 0u;
+    const uint32_t *wp = body_s + off;
+#pragma unroll
+    for (int j = 0; j < CWMAX; ++j) {
+        // every 8-column group starts on a 16-byte boundary of the stream (ktformat.cu): re-base when a warp crosses one
+        if (j == 8 && cw > 8) wp = body_s + (woff_s[(col0 + 8) >> 3] - woff_s[0]);
+        const int nw = (cwd[j >> 2] >> (8 * (j & 3))) & 0xFF;  // 0 for j >= cw
+        if (nw > 0) {
+            uint32_t word = *wp;
+#pragma unroll 1
+            for (int i = 1; i < nw; ++i) {
+                const uint32_t next = wp[i];
+                gather_word<NEG>(acc[j][0], acc[j][1], word, xbase);
+                word = next;
+            }
+            gather_word<NEG>(acc[j][0], acc[j][1], word, xbase);
+            wp += nw;
+        }
+    }
+}
+
+// work unit u -> (row tile, first column, columns per warp).  Units [0, units_full) are full 256-column tiles; the
+// remaining full tiles are cut into `sub` narrower units each so that the last round of the persistent grid is short.
+struct Unit {
+    int mt, n0, cw;
+};
+__device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) {
+    int fu = u, part = 0, cw = CWMAX;
+    if (u >= p.units_full) {
+        const int v = u - p.units_full;
+        fu = p.units_full + v / p.sub;
+        part = v % p.sub;
+        cw = CWMAX / p.sub;
+    }
+    Unit r;
+    r.mt = fu / p.ntiles;
+    r.cw = cw;
+    r.n0 = (fu % p.ntiles) * (CWMAX * NWARP) + part * (cw * NWARP);
+    return r;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int TN = CW * NWARP;
     const uint32_t stage_bytes = p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)stage_bytes);
     uint64_t *empty = full + 2;
@@ -135,16 +178,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     }
     __syncthreads();
 
-    const int units = p.mtiles * p.ntiles;
-
     if (warp >= NWARP) {
         // ===== producer warpgroup: hands its registers to the compute warpgroups; one thread feeds the two-stage ring =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
         if (warp == NWARP && lane == 0) {
             uint32_t it = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int mt = u / p.ntiles, nt = u % p.ntiles;
-                const int n0 = nt * TN;
+            for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+                const Unit un = decode_unit(p, u);
+                const int tn = un.cw * NWARP;
+                const uint32_t woff_copy = (uint32_t)(((tn / 8 + 1) * 4 + 15) & ~15);
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int c = 0; c < p.nchunk; ++c, ++it) {
                         const uint32_t s = it & 1u;
@@ -153,14 +195,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                         const int plane = pass * p.nchunk + c;
                         const int rows = min(p.kc, p.K - c * p.kc);
                         const uint32_t xbytes = (uint32_t)rows * (TM * 4);
-                        const size_t gidx = (size_t)plane * p.ngroup + (n0 >> 3);
-                        const uint32_t w0 = __ldg(p.woff + gidx), w1 = __ldg(p.woff + gidx + TN / 8);
+                        const size_t gidx = (size_t)plane * p.ngroup + (un.n0 >> 3);
+                        const uint32_t w0 = __ldg(p.woff + gidx), w1 = __ldg(p.woff + gidx + tn / 8);
                         const uint32_t bbytes = (w1 - w0) * 4u;
-                        constexpr uint32_t woff_copy = (((TN / 8 + 1) * 4) + 15) & ~15;
-                        mbar_arrive_expect_tx(&full[s], xbytes + bbytes + TN + woff_copy);
-                        bulk_g2s(st, p.XT + ((size_t)mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
+                        mbar_arrive_expect_tx(&full[s], xbytes + bbytes + tn + woff_copy);
+                        bulk_g2s(st, p.XT + ((size_t)un.mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
                         if (bbytes) bulk_g2s(st + p.xstage_bytes, p.body + w0, bbytes, &full[s]);
-                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + n0, TN, &full[s]);
+                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + un.n0, tn, &full[s]);
                         bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes + CNT_BYTES, p.woff + gidx, woff_copy, &full[s]);
                     }
                 }
@@ -169,89 +210,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         return;
     }
 
-    // ===== consumers: 16 warps x CW columns, 4 rows per lane =====
+    // ===== consumers: 16 warps x cw columns, 4 rows per lane =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
-    float acc[CW][4];
+    float2 acc[CWMAX][2];
     uint32_t it = 0;
     const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int mt = u / p.ntiles, nt = u % p.ntiles;
-        const int nbase = nt * TN + warp * CW;
-        const int mbase = mt * TM + lane * 4;
-        // the bias is re-read (L1/L2 hit) where it is needed instead of living in CW registers across the gather loops
+    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+        const Unit un = decode_unit(p, u);
+        const int cw = un.cw;
+        const int nbase = un.n0 + warp * cw;
+        const int mbase = un.mt * TM + lane * 4;
+        // the bias is re-read (L1/L2 hit) where it is needed instead of living in registers across the gather loops
         auto bias_of = [&](int j) { return (nbase + j < p.N) ? __ldg(p.B + nbase + j) : 0.f; };
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-            const float init = (p.order == TSG_ORDER_BIAS_FIRST) ? bias_of(j) : 0.f;  // tcsc.c:84 vs tcsc.c:149
-            acc[j][0] = init; acc[j][1] = init; acc[j][2] = init; acc[j][3] = init;
+        for (int j = 0; j < CWMAX; ++j) {
+            const float init = (p.order == TSG_ORDER_BIAS_FIRST && j < cw) ? bias_of(j) : 0.f;  // tcsc.c:84 vs tcsc.c:149
+            acc[j][0] = make_float2(init, init);
+            acc[j][1] = acc[j][0];
         }
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 1 && p.order == TSG_ORDER_SPLIT) {
                 // tcsc.c:125,138: Y = B + acc_pos is rounded and parked in Y, acc_neg starts from 0
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int m = mbase + v;
-                    if (m < p.M) {
+                for (int j = 0; j < CWMAX; ++j) {
+                    if (j < cw && nbase + j < p.N) {
+                        const float b = bias_of(j);
+                        const float t4[4] = {b + acc[j][0].x, b + acc[j][0].y, b + acc[j][1].x, b + acc[j][1].y};
 #pragma unroll
-                        for (int j = 0; j < CW; ++j)
-                            if (nbase + j < p.N) p.Y[(size_t)m * p.ldy + nbase + j] = bias_of(j) + acc[j][v];
+                        for (int v = 0; v < 4; ++v)
+                            if (mbase + v < p.M) p.Y[(size_t)(mbase + v) * p.ldy + nbase + j] = t4[v];
                     }
+                    acc[j][0] = make_float2(0.f, 0.f);
+                    acc[j][1] = acc[j][0];
                 }
-#pragma unroll
-                for (int j = 0; j < CW; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
             }
             const bool neg = (pass == 1) && (p.order != TSG_ORDER_SPLIT);
             for (int c = 0; c < p.nchunk; ++c, ++it) {
                 const uint32_t s = it & 1u;
                 mbar_wait(&full[s], (it >> 1) & 1u);
                 const uint8_t *st = smem + (size_t)s * stage_bytes;
-                const float *xs = reinterpret_cast<const float *>(st);
+                const uint32_t xbase = smem_addr(st) + lane * 16;
                 const uint32_t *body_s = reinterpret_cast<const uint32_t *>(st + p.xstage_bytes);
                 const uint8_t *cnt_s = st + p.xstage_bytes + p.body_stage_bytes;
                 const uint32_t *woff_s = reinterpret_cast<const uint32_t *>(cnt_s + CNT_BYTES);
-                if (neg) gather_chunk<CW, true>(acc, xs, cnt_s, woff_s, body_s, warp, lane);
-                else gather_chunk<CW, false>(acc, xs, cnt_s, woff_s, body_s, warp, lane);
+                if (neg) gather_chunk<true>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
+                else gather_chunk<false>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
         }
-        // ---- fused epilogue: bias, PReLU, store ----
+        // ---- fused epilogue: bias, PReLU, store (and, on the multi-GPU path, the same store into every peer's Y) ----
+        const bool full_vec = vec_ok && (cw % 4 == 0) && (nbase + cw <= p.N);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const int m = mbase + v;
             if (m >= p.M) continue;
             float *yrow = p.Y + (size_t)m * p.ldy + nbase;
-            float out[CW];
+            float out[CWMAX];
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                float y;
-                if (p.order == TSG_ORDER_BIAS_FIRST) y = acc[j][v];
-                else if (p.order == TSG_ORDER_BIAS_LAST) y = acc[j][v] + bias_of(j);                       // tcsc.c:161
-                else y = ((nbase + j < p.N) ? yrow[j] : 0.f) - acc[j][v];                               // tcsc.c:138
-                if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;                                          // tcsc.c:162
+            for (int j = 0; j < CWMAX; ++j) {
+                const float2 pr = acc[j][v >> 1];
+                const float av = (v & 1) ? pr.y : pr.x;
+                float y = av;
+                if (j < cw) {
+                    if (p.order == TSG_ORDER_BIAS_LAST) y = av + bias_of(j);                                   // tcsc.c:161
+                    else if (p.order == TSG_ORDER_SPLIT) y = ((nbase + j < p.N) ? yrow[j] : 0.f) - av;          // tcsc.c:138
+                    if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;                                              // tcsc.c:162
+                }
                 out[j] = y;
             }
-            if (vec_ok && CW % 4 == 0 && nbase + CW <= p.N) {
+            for (int q = -1; q < p.npeer; ++q) {  // q == -1: the local Y
+                float *row = (q < 0) ? yrow : p.peerY[q] + (size_t)m * p.ldy + nbase;
+                if (full_vec) {
 #pragma unroll
-                for (int j = 0; j < CW; j += 4)
-                    *reinterpret_cast<float4 *>(yrow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-                // fused all-gather: the same 64-byte row segment goes to every peer over NVLink (peer pointers share
-                // the local Y's alignment and pitch)
-                for (int q = 0; q < p.npeer; ++q) {
-                    float *prow = p.peerY[q] + (size_t)m * p.ldy + nbase;
+                    for (int j = 0; j < CWMAX; j += 4)
+                        if (j < cw) *reinterpret_cast<float4 *>(row + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                } else {
 #pragma unroll
-                    for (int j = 0; j < CW; j += 4)
-                        *reinterpret_cast<float4 *>(prow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < CW; ++j)
-                    if (nbase + j < p.N) yrow[j] = out[j];
-                for (int q = 0; q < p.npeer; ++q) {
-                    float *prow = p.peerY[q] + (size_t)m * p.ldy + nbase;
-#pragma unroll
-                    for (int j = 0; j < CW; ++j)
-                        if (nbase + j < p.N) prow[j] = out[j];
+                    for (int j = 0; j < CWMAX; ++j)
+                        if (j < cw && nbase + j < p.N) row[j] = out[j];
                 }
             }
         }
@@ -389,22 +426,19 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
     return dev_free(XS);
 }
 
-template <int CW>
 static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
-    const int units = p.mtiles * p.ntiles;
-    const int grid = units < num_sms() ? units : num_sms();
-    k_tcsc_gemm<CW><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
+    k_tcsc_gemm<<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_tcsc_gemm");
     return TSG_OK;
 }
 
 }  // namespace tsg
-
 using namespace tsg;
 
 namespace tsg {
@@ -418,6 +452,7 @@ int tsg_tcsc_set_kernel(int which) {
     g_force_kernel = which;
     return TSG_OK;
 }
+int tsg_tcsc_get_kernel(void) { return g_force_kernel; }
 
 int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                   long long ldy) {
@@ -454,20 +489,24 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
     const size_t smem_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES) + 64;
-    // column tile: 256 (CW=16) when that still gives every SM a few units, else narrower tiles for more parallelism
+    // unit decomposition: full 256-column tiles for as many complete rounds of the persistent grid as there are, the
+    // left-over tiles cut into 2 or 4 narrower units each so that the last round is short (tail balancing)
     const int sms = num_sms();
-    int rc;
-    auto units_for = [&](int cw) { return p.mtiles * ((N + 16 * cw - 1) / (16 * cw)); };
-    if (units_for(16) >= 2 * sms || units_for(8) <= units_for(16)) {
-        p.ntiles = (N + 255) / 256;
-        rc = launch_tiled<16>(p, smem_bytes);
-    } else if (units_for(8) >= sms || units_for(4) <= units_for(8)) {
-        p.ntiles = (N + 127) / 128;
-        rc = launch_tiled<8>(p, smem_bytes);
-    } else {
-        p.ntiles = (N + 63) / 64;
-        rc = launch_tiled<4>(p, smem_bytes);
+    p.ntiles = (N + 255) / 256;
+    const int U = p.mtiles * p.ntiles;
+    p.units_full = (U / sms) * sms;
+    const int R = U - p.units_full;
+    p.sub = 1;
+    if (R > 0) {
+        // cost of the tail in full-unit times for sub = 1, 2, 4 (narrower units re-stream X, so prefer the smaller sub on ties)
+        double best = (double)((R + sms - 1) / sms);
+        for (int sub = 2; sub <= 4; sub *= 2) {
+            const double cost = (double)((R * sub + sms - 1) / sms) / sub * (1.0 + 0.04 * sub);
+            if (cost < best - 1e-9) { best = cost; p.sub = sub; }
+        }
     }
+    p.units_total = p.units_full + R * p.sub;
+    int rc = launch_tiled(p, smem_bytes);
     int rc2 = dev_free(XT);
     return rc ? rc : rc2;
 }

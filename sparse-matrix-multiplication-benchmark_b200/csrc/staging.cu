@@ -56,11 +56,16 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
         TSG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     }
     TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
-    // slab: a multiple of 128 rows giving every SM a few work units; at least 4 slabs when M allows
-    int slab = 1024;
-    while (slab > 128 && (M + slab - 1) / slab < 4) slab >>= 1;
+    // slabs: multiples of 128 rows (the kernel's row tile), about 1024 rows each, at least 4 when M allows, balanced so
+    // that no tiny tail slab is left over
+    int nslab = (M + 1023) / 1024;
+    if (nslab < 4) nslab = (M + 127) / 128 < 4 ? (M + 127) / 128 : 4;
+    int slab = (((M + nslab - 1) / nslab) + 127) / 128 * 128;
     if (M < TSG_SKINNY_M) slab = M;
-    const int nslab = (M + slab - 1) / slab;
+    nslab = (M + slab - 1) / slab;
+    // one call = one kernel family: a short last slab must not drop into the skinny kernel (different summation order)
+    const int saved_kernel = tsg_tcsc_get_kernel();
+    if (saved_kernel == 0 && M >= TSG_SKINNY_M) tsg_tcsc_set_kernel(1);
     const int nbuf = nslab < 3 ? nslab : 3;
     float *dX[3] = {nullptr, nullptr, nullptr}, *dY[3] = {nullptr, nullptr, nullptr}, *dB = nullptr;
     cudaEvent_t ev_in[3], ev_k[3], ev_out[3];
@@ -68,7 +73,7 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     tsg_set_stream(s_k);
     int b_owned = 0;
     void *bdev = nullptr;
-    if ((rc = tsg_shim_stage_in(B_any, (size_t)N * 4, &bdev, &b_owned))) { tsg_set_stream(user); return rc; }
+    if ((rc = tsg_shim_stage_in(B_any, (size_t)N * 4, &bdev, &b_owned))) { tsg_set_stream(user); tsg_tcsc_set_kernel(saved_kernel); return rc; }
     dB = static_cast<float *>(bdev);
     for (int i = 0; i < nbuf && !rc; ++i) {
         rc = dev_alloc_t(&dX[i], (size_t)slab * K);
@@ -109,6 +114,7 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     tsg_shim_release(dB, b_owned);
     cudaStreamSynchronize(s_k);
     tsg_set_stream(user);
+    tsg_tcsc_set_kernel(saved_kernel);
     if (rc) return rc;
     if (e != cudaSuccess || e2 != cudaSuccess)
         return set_error(TSG_ECUDA, "pipelined GEMM failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));

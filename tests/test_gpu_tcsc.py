@@ -255,8 +255,14 @@ def test_full_size_cfg2(t, port):
     wo = port.tcsc_from_dense(Wd.cpu().numpy())
     yo = port.tcsc_sgemm_prelu_basic(X[rows].cpu().numpy(), wo, B.cpu().numpy(), 0.2)
     assert np.array_equal(Y[rows].cpu().numpy(), yo)
+    # fp64 dense check on another slice.  Y is bit-identical to the reference, so its distance to the fp64 result IS the
+    # reference's own (strictly sequential fp32 summation of ~410 terms: ~1.5e-5 at this size); the bar is
+    # max(1e-5, reference's own error), both printed.
     rel, ab = t.verify_dense_f64(X, Wd, B, Y, a=0.2, use_prelu=True, m0=1000, mrows=64)
-    assert rel <= TOL, (rel, ab)
+    xs, bs = X[1000:1064].cpu().numpy(), B.cpu().numpy()
+    rel_ref = rel_err(port.tcsc_sgemm_prelu_basic(xs, wo, bs, 0.2), port.tcsc_sgemm_f64(xs, wo, bs, 0.2))
+    print(f"cfg2 rows 1000..1063: ours vs fp64 {rel:.3e} (abs {ab:.3e}); reference vs fp64 {rel_ref:.3e}")
+    assert rel <= max(TOL, rel_ref * (1 + 1e-6)), (rel, rel_ref)
     Z0 = torch.zeros((N,), device="cuda")
     Y1, Y2 = torch.empty_like(Y), torch.empty_like(Y)
     w.gemm(X, Z0, Y1)
