@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native sparse ternary GEMM  Y = PReLU(X*W + b)  (TCSC).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1] [--dist-mode 0|1]
+
+Prints ONE JSON line on rank 0 (contract in the task statement).  Metric = BASELINE.json's "sparse GEMM GFLOP/s-equiv"
+under the reference's own FLOP model 2*M*nnz + M*N (main.cpp:47-51).
+
+N = 1   workload = BASELINE.json configs[1]: TCSC sparseGEMM+bias+PReLU, M=K=N=4096, 90 % sparsity, synthetic ternary W
+        (P(+1)=P(-1)=5 %), X,b ~ U[-1,1), a = 0.2; inputs resident in HBM; four X/Y buffer sets (512 MiB) are rotated so
+        that every step streams X and Y from HBM rather than from the 126 MB L2.
+N > 1   the column-partitioned path of north_star (3), weak scaling: every GPU owns 4096 columns of a 4096 x (4096*N) W,
+        X is broadcast from rank 0 and every rank ends with the full M x (4096*N) Y (fused peer-store all-gather by
+        default, --dist-mode 0 for ncclAllGather + re-layout).  At N = 1 this degenerates to the workload above.
+`value`   whole-job throughput, device-timed (CUDA events), barrier + synchronize on both sides, max over ranks.
+`e2e`     the same metric through the reference-named C entry point tcsc_sgemm_prelu_basic with HOST (pinned) buffers:
+          host->device copy of X and b and device->host copy of Y inside the timed region, every step.
+`roofline` dominant kernel k_tcsc_gemm: achieved = M*nnz gather-adds / its CUDA-event time measured inside the timed
+          region, against the FP32-add peak (#SM x 128 lanes x max SM clock) -- the path is FP32-add/shared-memory bound
+          at this shape, not HBM bound; the HBM view (algorithmic bytes / time vs the measured copy
+          bandwidth of MEASURED_PEAKS.json) and the shared-memory gather ceiling are reported next to it.
+`cpu_baseline` the unmodified reference (oracle/_ref, kind "reference"; else the oracle port) timed on this box's host
+          cores on a bounded row sample of the same workload.
+--impl reference   times the reference's own CPU implementation of the path (single thread -- sparse/tcsc.c has no
+          threading) on bounded row samples of the same workload and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (M, K, N_per_gpu, num, den, description)
+    "cfg2": (4096, 4096, 4096, 1, 10, "TCSC sparseGEMM+PReLU M=4096 K=4096 N=4096 90% sparsity (BASELINE.json configs[1])"),
+    "cfg1": (64, 512, 512, 1, 2, "TCSC sparseGEMM+bias+PReLU M=64 K=512 N=512 50% sparsity (BASELINE.json configs[0])"),
+    "cfg4": (8192, 4096, 14336, 1, 3, "ternary LLM-layer shape M=8192 K=4096 N=14336 66% sparsity (BASELINE.json configs[3])"),
+}
+ALPHA = 0.2  # main.cpp:268
+SEED_W, SEED_X, SEED_B = 42, 43, 44
+METRIC = "sparse GEMM GFLOP/s-equiv (2*M*nnz + M*N per call, TCSC+bias+PReLU fp32)"
+UNIT = "GFLOP/s-equiv"
+
+
+def flops_equiv(M, N, nnz):
+    return 2.0 * M * nnz + 1.0 * M * N  # main.cpp:47-51
+
+
+def algorithmic_bytes(M, K, N, nnz):
+    return 4.0 * M * K + 4.0 * M * N + 4.0 * nnz + 8.0 * (N + 1) + 4.0 * N
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "MEASURED_PEAKS.json"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- clocks / throttle reasons during the timed region ------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.max_mhz, self.thread, self.ok = None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        if self.thread:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        busy = [m for m, u in self.samples if u >= 50] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# =====================================================================================================================
+# reference arm / CPU baseline
+# =====================================================================================================================
+def cpu_reference_backend():
+    from oracle import pyoracle
+    if pyoracle.ref_available("native") and pyoracle.ref_native_runs():
+        r = pyoracle.Ref("native")
+        return r, "reference", r.build_flags
+    if pyoracle.ref_available(""):
+        r = pyoracle.Ref("")
+        return r, "reference", r.build_flags + " (portable build: the -march=native objects do not run on this host)"
+    return pyoracle.Port(), "port", "gcc -O2 -ffp-contract=off (oracle/tsg_oracle.c restatement; oracle/_ref absent)"
+
+
+def pin_one_core():
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[-1]})
+    except Exception:
+        pass
+
+
+def cpu_pick_rows(backend, W, M, K, N, seconds_target, port):
+    """Rows of the workload one timed call should cover so that it lasts about `seconds_target` (probe: 8 rows)."""
+    B = port.gen_uniform((N,), SEED_B)
+    probe = min(M, 8)
+    Xp = port.gen_uniform((probe, K), SEED_X)  # counter-based generator: rows 0..probe-1 of the workload's X
+    t_probe = backend.time_prelu_basic(Xp, W, B, ALPHA, reps=2)
+    rows = int(max(probe, min(M, seconds_target / max(t_probe / probe, 1e-9))))
+    return min(rows, M)
+
+
+def cpu_time_rows(backend, W, rows, K, N, port):
+    """One call of tcsc_sgemm_prelu_basic (sparse/tcsc.c:143-165) on rows 0..rows-1 of the workload; seconds."""
+    X = port.gen_uniform((rows, K), SEED_X)
+    B = port.gen_uniform((N,), SEED_B)
+    return backend.time_prelu_basic(X, W, B, ALPHA, reps=1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.pyoracle import Port
+    port = Port()
+    M, K, Ng, num, den, desc = WORKLOADS[args.workload]
+    N = Ng * max(1, args.gpus)
+    backend, kind, flags = cpu_reference_backend()
+    pin_one_core()  # one thread pinned to one core, as benchmark.sh:36 does
+    Wd = port.gen_ternary(K, N, SEED_W, num, den)
+    W = backend.tcsc_from_dense(Wd)
+    nnz = W.nnz
+    # bounded sample per step so that (steps + warmup) steps end within ~2 minutes
+    per_step = max(0.5, min(6.0, 110.0 / max(1, args.steps + args.warmup)))
+    rows = cpu_pick_rows(backend, W, M, K, N, per_step, port)
+    secs_list = []
+    for i in range(args.warmup + args.steps):
+        secs = cpu_time_rows(backend, W, rows, K, N, port)
+        if i >= args.warmup:
+            secs_list.append(secs)
+    mean_s = sum(secs_list) / len(secs_list)
+    value = flops_equiv(rows, N, nnz) / mean_s / 1e9
+    sample = f"rows 0..{rows - 1} of {M} (all {N} columns, K={K}), one call per step, 1 thread pinned; the m-outer loop nest is linear in M"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc if args.gpus <= 1 else f"{desc}; N scaled to {N} columns for {args.gpus} GPUs", "M": M, "K": K, "N": N,
+                   "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA, "function": "tcsc_sgemm_prelu_basic (sparse/tcsc.c:143-165)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "build": flags,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != max(1, args.gpus):
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    t = ge.load()
+    t.lib()  # raises if libtsgemm_b200.so is missing: there is no fallback
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t.use_torch_stream()
+
+    M, K, Ng, num, den, desc = WORKLOADS[args.workload]
+    N = Ng * world
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+
+    # ---- W: this rank's column slice, generated and converted on the device ----
+    D = None
+    if world > 1:
+        D = t.Dist(rank, world)
+        col0, ncols = D.partition(N)
+    else:
+        col0, ncols = 0, N
+    Wd = t.gen_ternary_slice(K, N, col0, ncols, SEED_W, num, den) if world > 1 else t.gen_ternary(K, N, SEED_W, num, den)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    W = t.DeviceTcsc.from_dense(Wd)
+    ev[1].record()
+    info = W.stream_info()
+    ev[2].record()
+    torch.cuda.synchronize()
+    convert_ms, stream_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    nnz_local = W.nnz
+    nnz_t = torch.tensor([nnz_local], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz = int(nnz_t.item())
+
+    # ---- inputs resident in HBM; rotate buffer sets so that each step streams from HBM, not L2 ----
+    nsets = 4 if (M * K + M * N) * 4 * 4 <= 8 << 30 else 2
+    Xs = [t.gen_uniform((M, K), SEED_X + 100 * i) for i in range(nsets)]
+    B = t.gen_uniform((N,), SEED_B)
+    if world > 1 and args.dist_mode == 1:
+        Ys = [D.alloc_y(M, N)]  # symmetric buffer for the fused peer-store all-gather
+    else:
+        Ys = [torch.empty((M, N), device="cuda") for _ in range(nsets)]
+
+    def step(i):
+        X, Y = Xs[i % len(Xs)], Ys[i % len(Ys)]
+        if world > 1:
+            D.gemm(W, X, B, Y, N, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST, root=0, mode=args.dist_mode)
+        else:
+            W.gemm(X, B, Y, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t.profile_enable(True)
+    t.profile_read()
+    t.launch_count(reset=True)
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev[1].record()
+    barrier()
+    launches = t.launch_count(reset=True)
+    kern_ms_total, kern_launches = t.profile_read()
+    t.profile_enable(False)
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    el = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = flops_equiv(M, N, nnz) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (this rank's launches) ----
+    kern_ms = kern_ms_total / max(1, kern_launches)
+    adds_per_launch = float(M) * nnz_local
+    fadd_peak = 148 * 128 * sm_max_mhz * 1e6 / 1e12  # Tadd/s
+    achieved_tadd = adds_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    bytes_per_launch = algorithmic_bytes(M, K, ncols, nnz_local)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32_add", "kernel": "k_tcsc_gemm", "kernel_ms": kern_ms, "kernel_launches_timed": kern_launches,
+        "achieved": achieved_tadd, "peak": fadd_peak, "unit": "Tadd/s", "frac": achieved_tadd / fadd_peak,
+        "peak_source": f"#SM(148) x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (max SM clock, {peak_src}); microbenchmark: 0.99 of it reached by a register-only FADD loop",
+        "algorithmic_adds_per_launch": adds_per_launch, "traffic": traffic,
+        "hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (bytes_per_launch / (kern_ms * 1e-3) / 1e9) / hbm_peak if kern_ms > 0 else 0.0, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "peak_source": peak_src},
+        "smem_gather": {"achieved": achieved_tadd, "peak": fadd_peak / 4, "unit": "Tadd/s", "frac": achieved_tadd / (fadd_peak / 4),
+                        "note": "one LDS word per add: 128 B/clk/SM shared-memory crossbar = 1/4 of the FP32-add peak (profiles/microbench)"},
+    }
+
+    # ---- e2e: host buffers through the reference-named C entry point ----
+    e2e = None
+    cpu_baseline = None
+    if world == 1:
+        Wd_host = Wd.cpu().numpy()
+        Wh = t.tcsc_from_dense(Wd_host)  # host tcsc_t + cached device mirror, as a reference caller would hold it
+        Xh = [torch.empty((M, K), dtype=torch.float32).pin_memory() for _ in range(2)]
+        Yh = [torch.empty((M, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+        for i in range(2):
+            Xh[i].copy_(Xs[i].cpu())
+        Bh = B.cpu().numpy()
+        e2e_steps = max(3, min(args.steps, 20))
+        for i in range(2):
+            t.tcsc_sgemm_prelu_basic(Xh[i % 2].numpy(), Wh, Bh, ALPHA, Y=Yh[i % 2].numpy())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            t.tcsc_sgemm_prelu_basic(Xh[i % 2].numpy(), Wh, Bh, ALPHA, Y=Yh[i % 2].numpy())  # returns with Y in host memory
+        t1 = time.perf_counter()
+        e2e_ms = (t1 - t0) * 1e3 / e2e_steps
+        same = bool(torch.equal(Yh[0], Ys[0].cpu()))  # host-pointer path and device-resident path: same bits
+        e2e = {"matches_device_resident_result": same, "value": flops_equiv(M, N, nnz) / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": 4 * M * K + 4 * N, "d2h_bytes_per_step": 4 * M * N,
+               "api": "tcsc_sgemm_prelu_basic(X_host, W, B_host, a, Y_host, M, N, K): pinned host buffers, row slabs pipelined H2D/kernel/D2H"}
+        Wh.free()
+    else:
+        # rank 0 owns X and wants the full Y in host memory: H2D, broadcast + partitioned GEMM + all-gather, D2H
+        Xh = torch.empty((M, K), dtype=torch.float32).pin_memory() if rank == 0 else None
+        Yh = torch.empty((M, N), dtype=torch.float32).pin_memory() if rank == 0 else None
+        if rank == 0:
+            Xh.copy_(Xs[0].cpu())
+        e2e_steps = max(3, min(args.steps, 10))
+        Xd = torch.empty((M, K), device="cuda")
+
+        def e2e_step():
+            if rank == 0:
+                Xd.copy_(Xh, non_blocking=True)
+            D.gemm(W, Xd, B, Ys[0], N, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST, root=0, mode=args.dist_mode)
+            if rank == 0:
+                Yh.copy_(Ys[0], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        t1 = time.perf_counter()
+        e2e_ms_t = torch.tensor([(t1 - t0) * 1e3 / e2e_steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(e2e_ms_t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(e2e_ms_t.item())
+        e2e = {"value": flops_equiv(M, N, nnz) / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": 4 * M * K, "d2h_bytes_per_step": 4 * M * N,
+               "api": "rank 0: pinned X -> device, tsg_dist_gemm (X broadcast, column-partitioned GEMM, Y all-gather), full Y -> pinned host"}
+    clocks = sampler.stop()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        from oracle.pyoracle import Port
+        backend, kind, flags = cpu_reference_backend()
+        port = Port()
+        pin_one_core()
+        Wc = backend.tcsc_from_dense(Wd_host)
+        nnz_c = Wc.nnz
+        rows = cpu_pick_rows(backend, Wc, M, K, N, 12.0, port)
+        secs = cpu_time_rows(backend, Wc, rows, K, N, port)
+        cpu_baseline = {"value": flops_equiv(rows, N, nnz_c) / secs / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": f"rows 0..{rows - 1} of {M} (all {N} columns), 1 call, {secs:.2f} s, 1 thread pinned (benchmark.sh:36)",
+                        "build": flags, "host_cores_available": os.cpu_count(), "seconds_for_full_M_extrapolated": secs * M / rows}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc if world == 1 else f"{desc}, per GPU: {world} x {Ng} = {N} columns N-sharded, X broadcast from rank 0, "
+                                                            f"Y all-gathered ({'fused NVLink peer stores' if args.dist_mode == 1 else 'ncclAllGather + re-layout'})",
+                       "M": M, "K": K, "N": N, "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA,
+                       "order": "tcsc_sgemm_prelu_basic (0, +pos asc, -neg asc, +b, PReLU) -- bit-identical to the reference",
+                       "l2": f"{len(Xs)} X buffers{'' if len(Ys) == 1 else f' and {len(Ys)} Y buffers'} rotated ({(len(Xs) * M * K + len(Ys) * M * N) * 4 >> 20} MiB > 126 MB L2)",
+                       "gather_stream": info, "convert_dense_to_tcsc_ms": convert_ms, "build_gather_stream_ms": stream_ms,
+                       "seeds": {"W": SEED_W, "X": SEED_X, "b": SEED_B}},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "gadd_per_s": float(M) * nnz / (ms_per_step * 1e-3) / 1e9,
+            "dense_equiv_gflops": 2.0 * M * K * N / (ms_per_step * 1e-3) / 1e9,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        if D is not None:
+            torch.cuda.synchronize()
+            D.destroy()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--dist-mode", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -84,6 +84,9 @@ int tsg_tcsc_gemm(tsg_tcsc *W, const float *X_dev, const float *B_dev, float a, 
 /* force one kernel: 0 auto, 1 tiled shared-memory gather kernel, 2 skinny kernel */
 int tsg_tcsc_set_kernel(int which);
 int tsg_tcsc_get_kernel(void);
+/* per-launch CUDA-event timing of the tiled GEMM kernel on its launching stream (bench.py's roofline numerator) */
+int tsg_profile_enable(int on);
+int tsg_profile_read(double *total_ms, int *launches);
 
 /* ---- BCSR device mirror --------------------------------------------------------------------------------------- */
 typedef struct tsg_bcsr tsg_bcsr;

@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
     L.tsg_tcsc_stream_info.argtypes = [vp, C.POINTER(ll), ip, ip]
     L.tsg_tcsc_gemm.argtypes = [vp, vp, vp, f, i, i, vp, i, i, i, ll]
     L.tsg_tcsc_set_kernel.argtypes = [i]
+    L.tsg_profile_enable.argtypes = [i]
+    L.tsg_profile_read.argtypes = [C.POINTER(C.c_double), ip]
     L.tsg_bcsr_from_dense_f32.argtypes = [vp, i, i, i, i, C.POINTER(vp)]
     L.tsg_bcsr_from_arrays.argtypes = [vp, vp, vp, i, i, i, i, i, C.POINTER(vp)]
     L.tsg_bcsr_destroy.argtypes, L.tsg_bcsr_destroy.restype = [vp], None
@@ -144,6 +146,17 @@ def use_torch_stream() -> None:
     """Point the library at torch's current CUDA stream (call after torch.cuda.set_device / inside a stream ctx)."""
     import torch
     lib().tsg_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+def profile_enable(on: bool) -> None:
+    lib().tsg_profile_enable(int(on))
+
+
+def profile_read():
+    """(total device ms, launches) of the tiled GEMM kernel since the last call."""
+    ms, n = C.c_double(), C.c_int()
+    lib().tsg_profile_read(C.byref(ms), C.byref(n))
+    return ms.value, n.value
 
 
 def launch_count(reset: bool = False) -> int:

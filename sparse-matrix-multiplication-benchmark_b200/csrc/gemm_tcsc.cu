@@ -21,6 +21,8 @@
 // Skinny kernel (M < TSG_SKINNY_M, the decode shape): HBM/L2-bound on the index stream.  One warp per column, lanes
 // stride over the column's non-zeros (coalesced index loads), gather up to 8 rows of X per index from a K-major copy
 // of X, tree-reduce across the warp.
+#include <vector>
+
 #include "tsg_internal.h"
 
 namespace tsg {
@@ -401,6 +403,8 @@ __global__ void __launch_bounds__(256) k_tcsc_skinny(const float *__restrict__ X
 }
 
 static thread_local int g_force_kernel = 0;
+static thread_local int g_profile = 0;
+static thread_local std::vector<cudaEvent_t> g_prof_events;
 
 static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy) {
     cudaStream_t st = stream();
@@ -433,8 +437,19 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
         attr_set = true;
     }
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_profile) {  // bench.py: device time of this kernel alone, measured on the launching stream
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream());
+    }
     k_tcsc_gemm<<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_tcsc_gemm");
+    if (g_profile) {
+        cudaEventRecord(e1, stream());
+        g_prof_events.push_back(e0);
+        g_prof_events.push_back(e1);
+    }
     return TSG_OK;
 }
 
@@ -453,6 +468,28 @@ int tsg_tcsc_set_kernel(int which) {
     return TSG_OK;
 }
 int tsg_tcsc_get_kernel(void) { return g_force_kernel; }
+
+// per-launch device timing of the tiled GEMM kernel (CUDA events on the launching stream)
+int tsg_profile_enable(int on) {
+    g_profile = on;
+    return TSG_OK;
+}
+// synchronises, sums the elapsed time of every tiled-kernel launch recorded since the last call, clears the list
+int tsg_profile_read(double *total_ms, int *launches) {
+    double tot = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < g_prof_events.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventSynchronize(g_prof_events[i + 1]);
+        if (cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]) == cudaSuccess) { tot += ms; ++n; }
+        cudaEventDestroy(g_prof_events[i]);
+        cudaEventDestroy(g_prof_events[i + 1]);
+    }
+    g_prof_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return TSG_OK;
+}
 
 int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                   long long ldy) {

@@ -1,0 +1,136 @@
+"""The column-partitioned multi-GPU path.
+
+CPU part (gloo, world_size 2, runs everywhere): the partition arithmetic, the rule that re-assembles the global
+bit-exact TCSC from per-rank slices, and slab re-assembly of Y through a real all_gather -- with the
+oracle standing in for the per-rank kernel, so only the host-side logic is under test.
+GPU part (needs >= 2 GPUs): the real thing, both exchange modes, bit-exact against the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import __graft_entry__ as ge
+
+ROOT = ge.ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port_no, M, K, N, q):
+    sys.path.insert(0, ROOT)
+    from oracle.pyoracle import Port
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = ge.load()
+    port = Port()
+    c0, nc = t.partition(N, rank, world)
+    Wd = port.gen_ternary(K, N, 42, 1, 4)
+    X = port.gen_uniform((M, K), 43) if rank == 0 else np.zeros((M, K), np.float32)
+    B = port.gen_uniform((N,), 44)
+    xt = torch.from_numpy(X)
+    dist.broadcast(xt, src=0)                                  # X broadcast
+    wl = port.tcsc_from_dense(np.ascontiguousarray(Wd[:, c0:c0 + nc]))  # rank-local conversion of its column slice
+    yl = port.tcsc_sgemm_prelu_basic(xt.numpy(), wl, B[c0:c0 + nc], 0.2)
+    # Y all-gather: slabs padded to the widest rank, then re-laid out with the library's partition rule
+    widths = [t.partition(N, r, world)[1] for r in range(world)]
+    wmax = max(widths)
+    slab = torch.zeros((M, wmax))
+    slab[:, :nc] = torch.from_numpy(yl)
+    out = [torch.zeros((M, wmax)) for _ in range(world)]
+    dist.all_gather(out, slab)
+    Y = np.concatenate([out[r][:, :widths[r]].numpy() for r in range(world)], axis=1)
+    # global TCSC = concatenated row-index arrays + column pointers rebased by the exclusive prefix of (n_pos, n_neg)
+    counts = torch.tensor([wl.n_elem_pos, wl.n_elem_neg])
+    allc = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    pre_p = sum(int(allc[r][0]) for r in range(rank))
+    pre_n = sum(int(allc[r][1]) for r in range(rank))
+    q.put((rank, Y, wl.col_start_pos[:-1] + pre_p, wl.col_start_neg[:-1] + pre_n, wl.row_index_pos, wl.row_index_neg))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N", [96, 200])
+def test_gloo_two_ranks_partition_and_reassembly(N):
+    from oracle.pyoracle import Port
+    world, M, K = 2, 5, 64
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port_no, M, K, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    port = Port()
+    Wd = port.gen_ternary(K, N, 42, 1, 4)
+    wg = port.tcsc_from_dense(Wd)
+    Yref = port.tcsc_sgemm_prelu_basic(port.gen_uniform((M, K), 43), wg, port.gen_uniform((N,), 44), 0.2)
+    for _, Y, *_ in res:
+        assert np.array_equal(Y, Yref)                       # every rank holds the full, bit-identical Y
+    csp = np.concatenate([r[2] for r in res] + [[wg.n_elem_pos]])
+    csn = np.concatenate([r[3] for r in res] + [[wg.n_elem_neg]])
+    assert np.array_equal(csp, wg.col_start_pos) and np.array_equal(csn, wg.col_start_neg)
+    assert np.array_equal(np.concatenate([r[4] for r in res]), wg.row_index_pos)
+    assert np.array_equal(np.concatenate([r[5] for r in res]), wg.row_index_neg)
+
+
+# ---- real multi-GPU run ------------------------------------------------------------------------------------------------
+def _gpu_worker(rank, world, port_no, M, K, N, mode, q):
+    sys.path.insert(0, ROOT)
+    from oracle.pyoracle import Port
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    t = ge.load()
+    t.lib()
+    t.use_torch_stream()
+    D = t.Dist(rank, world)
+    c0, nc = D.partition(N)
+    W = t.DeviceTcsc.from_dense(t.gen_ternary_slice(K, N, c0, nc, 42, 1, 4))
+    X = t.gen_uniform((M, K), 43) if rank == 0 else torch.zeros((M, K), device="cuda")
+    B = t.gen_uniform((N,), 44)
+    Y = D.alloc_y(M, N) if mode == 1 else torch.empty((M, N), device="cuda")
+    for _ in range(2):  # twice: the second run overwrites a Y that peers have already read
+        D.gemm(W, X, B, Y, N, a=0.2, use_prelu=True, root=0, mode=mode)
+    torch.cuda.synchronize()
+    q.put((rank, Y.cpu().numpy()))
+    dist.barrier()
+    D.destroy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["nccl_allgather", "fused_peer_stores"])
+def test_two_gpus_bit_exact(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle.pyoracle import Port
+    world, M, K, N = 2, 256, 512, 1000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port_no, M, K, N, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    port = Port()
+    wg = port.tcsc_from_dense(port.gen_ternary(K, N, 42, 1, 4))
+    Yref = port.tcsc_sgemm_prelu_basic(port.gen_uniform((M, K), 43), wg, port.gen_uniform((N,), 44), 0.2)
+    for _, Y in res:
+        assert np.array_equal(Y, Yref)
