@@ -119,27 +119,26 @@ __device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t x
     uint32_t off = woff_s[col0 >> 3] - woff_s[0];
     if (col0 & 7) {  // cw == 4: the warp starts in the middle of an 8-column group
         const uint32_t prev = *reinterpret_cast<const uint32_t *>(cnt_s + (col0 & ~7));
-        off += __vsadu4(prev, 0u);
+        off += 4u * __vsadu4(prev, 0u);
     }
     uint32_t cwd[CWMAX / 4];
 #pragma unroll
     for (int i = 0; i < CWMAX / 4; ++i) cwd[i] = (4 * i < cw) ? *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i) : 0u;
-    const uint32_t *wp = body_s + off;
+    const uint4 *qp = reinterpret_cast<const uint4 *>(body_s + off);  // every list starts on a 16-byte boundary
 #pragma unroll
     for (int j = 0; j < CWMAX; ++j) {
-        // every 8-column group starts on a 16-byte boundary of the stream (ktformat.cu): re-base when a warp crosses one
-        if (j == 8 && cw > 8) wp = body_s + (woff_s[(col0 + 8) >> 3] - woff_s[0]);
-        const int nw = (cwd[j >> 2] >> (8 * (j & 3))) & 0xFF;  // 0 for j >= cw
-        if (nw > 0) {
-            uint32_t word = *wp;
+        const int nq = (cwd[j >> 2] >> (8 * (j & 3))) & 0xFF;  // 0 for j >= cw
 #pragma unroll 1
-            for (int i = 1; i < nw; ++i) {
-                const uint32_t next = wp[i];
-                gather_word<NEG>(acc[j][0], acc[j][1], word, xbase);
-                word = next;
+        for (int i = 0; i < nq; ++i) {
+            const uint4 w = *qp++;  // one uniform-address LDS.128 = up to 16 non-zeros
+            gather_word<NEG>(acc[j][0], acc[j][1], w.x, xbase);
+            if (w.y != 0xFFFFFFFFu) {  // entries are packed from the front: an all-padding word ends the list
+                gather_word<NEG>(acc[j][0], acc[j][1], w.y, xbase);
+                if (w.z != 0xFFFFFFFFu) {
+                    gather_word<NEG>(acc[j][0], acc[j][1], w.z, xbase);
+                    if (w.w != 0xFFFFFFFFu) gather_word<NEG>(acc[j][0], acc[j][1], w.w, xbase);
+                }
             }
-            gather_word<NEG>(acc[j][0], acc[j][1], word, xbase);
-            wp += nw;
         }
     }
 }
