@@ -129,7 +129,10 @@ int tsg_dist_barrier(tsg_dist *D);
  * bias (N); X_dev is valid on `root` and is broadcast in place (root < 0: every rank already holds X).
  * mode 0: the kernel writes a contiguous slab, ncclAllGather of the slabs, re-layout kernel into row-major Y.
  * mode 1: Y_dev must be the tsg_dist_alloc_y buffer; the kernel epilogue stores every finished row segment into
- *         the local Y and straight into every peer's Y over NVLink (fused all-gather). */
+ *         the local Y and straight into every peer's Y over NVLink (fused all-gather).
+ * mode 2: Y_dev must be the tsg_dist_alloc_y buffer; the kernel writes the local slab and bumps a progress counter
+ *         per 128-row tile; per peer a copy stream waits on those counters (cuStreamWaitValue32, no SM involved) and
+ *         pushes finished row blocks with strided 2-D DMA copies, so the all-gather overlaps the GEMM (M >= 32). */
 int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X_dev, int root, const float *B_dev, float a, int use_prelu,
                   int order, float *Y_dev, int M, int N, int K, int mode);
 

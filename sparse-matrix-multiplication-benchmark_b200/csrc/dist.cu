@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <vector>
 
 #include "tsg_internal.h"
 
@@ -85,9 +86,17 @@ __global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict_
 
 using namespace tsg;
 
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+
 struct tsg_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // mode 2: copy-engine all-gather overlapped with the kernel
+    unsigned int *done = nullptr;        // [max row tiles] progress counters written by the kernel
+    int done_cap = 0;
+    cudaStream_t copy_stream[TSG_MAX_PEERS] = {nullptr};
+    cudaEvent_t ev_start = nullptr, ev_copy[TSG_MAX_PEERS] = {nullptr};
+    StreamWaitValue32Fn wait_value = nullptr;
     // fused mode: symmetric Y buffer + peer mappings
     float *y_local = nullptr;
     size_t y_bytes = 0;
@@ -157,6 +166,12 @@ void tsg_dist_destroy(tsg_dist *D) {
     cudaDeviceSynchronize();
     dist_unmap(D);
     if (D->flag) cudaFree(D->flag);
+    if (D->done) cudaFree(D->done);
+    for (int p = 0; p < TSG_MAX_PEERS; ++p) {
+        if (D->copy_stream[p]) cudaStreamDestroy(D->copy_stream[p]);
+        if (D->ev_copy[p]) cudaEventDestroy(D->ev_copy[p]);
+    }
+    if (D->ev_start) cudaEventDestroy(D->ev_start);
     if (D->comm) g_nccl.CommDestroy(D->comm);
     delete D;
 }
@@ -226,8 +241,61 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         }
         // every rank must have finished READING its previous Y before a peer overwrites it
         TSG_TRY(tsg_dist_barrier(D));
-        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers));
+        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr));
         return tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
+    }
+
+    if (mode == 2) {
+        // (2) one persistent kernel writes the local slab and bumps a progress counter per 128-row tile;
+        // (3) per peer, a copy stream waits (stream memory op, no SM involved) until a block of row tiles is complete
+        //     and pushes it with a strided 2-D DMA copy over NVLink -- the all-gather runs on the copy engines while
+        //     the gather-add is still in flight.
+        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 2): Y must be the buffer returned by tsg_dist_alloc_y");
+        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 2): Y buffer too small");
+        if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 2) needs M >= %d", TSG_SKINNY_M);
+        const int mtiles = (M + 127) / 128;
+        if (!D->wait_value) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+                return set_error(TSG_EUNSUPPORTED, "cuStreamWaitValue32 is not available");
+            D->wait_value = reinterpret_cast<StreamWaitValue32Fn>(fn);
+            TSG_CUDA(cudaEventCreateWithFlags(&D->ev_start, cudaEventDisableTiming));
+            for (int p = 0; p < D->world; ++p) {
+                TSG_CUDA(cudaStreamCreateWithFlags(&D->copy_stream[p], cudaStreamNonBlocking));
+                TSG_CUDA(cudaEventCreateWithFlags(&D->ev_copy[p], cudaEventDisableTiming));
+            }
+        }
+        if (D->done_cap < mtiles) {
+            if (D->done) cudaFree(D->done);
+            TSG_CUDA(cudaMalloc(&D->done, sizeof(unsigned int) * mtiles));
+            D->done_cap = mtiles;
+        }
+        std::vector<unsigned int> targets(mtiles, 0u);
+        TSG_CUDA(cudaMemsetAsync(D->done, 0, sizeof(unsigned int) * mtiles, st));
+        TSG_TRY(tsg_dist_barrier(D));  // peers have finished reading their previous Y
+        TSG_CUDA(cudaEventRecord(D->ev_start, st));
+        if (ncols > 0)
+            TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 0, nullptr, D->done, targets.data()));
+        const int group = 4;  // row tiles per copy: 512 rows x ncols floats
+        for (int p = 1; p < D->world && ncols > 0; ++p) {
+            const int q = (D->rank + p) % D->world;
+            cudaStream_t cs = D->copy_stream[q];
+            TSG_CUDA(cudaStreamWaitEvent(cs, D->ev_start, 0));
+            for (int g0 = 0; g0 < mtiles; g0 += group) {
+                const int g1 = (g0 + group < mtiles) ? g0 + group : mtiles;
+                for (int mt = g0; mt < g1; ++mt) {
+                    int rc = D->wait_value(cs, (unsigned long long)(uintptr_t)(D->done + mt), targets[mt], /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
+                    if (rc != 0) return set_error(TSG_ECUDA, "cuStreamWaitValue32 failed (%d)", rc);
+                }
+                const int r0 = g0 * 128, r1 = (g1 * 128 < M) ? g1 * 128 : M;
+                TSG_CUDA(cudaMemcpy2DAsync(D->y_peer[q] + (size_t)r0 * N + col0, (size_t)N * 4, Y + (size_t)r0 * N + col0, (size_t)N * 4,
+                                           (size_t)ncols * 4, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, cs));
+            }
+            TSG_CUDA(cudaEventRecord(D->ev_copy[q], cs));
+            TSG_CUDA(cudaStreamWaitEvent(st, D->ev_copy[q], 0));
+        }
+        return tsg_dist_barrier(D);  // every rank's pushes have completed => every Y is whole
     }
 
     // mode 0: (2) contiguous slab, (3) ncclAllGather + re-layout

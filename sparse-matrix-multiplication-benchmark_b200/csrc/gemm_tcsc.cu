@@ -54,6 +54,9 @@ struct GemmParams {
     // (NVLink peer mappings, already offset to this rank's first column); 0 = single GPU
     int npeer;
     float *peerY[TSG_MAX_PEERS];
+    // progress counters, one per 128-row tile: every compute warp bumps done[mt] once its part of a unit is stored, so
+    // that stream-ordered peer copies (dist.cu, mode 2) can start on finished row blocks while the kernel still runs
+    unsigned int *done;
 };
 
 // ---- PTX helpers ----------------------------------------------------------------------------------------------------
@@ -293,6 +296,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 }
             }
         }
+        if (p.done) {  // publish: this warp's share of unit (mt, n0) is in memory
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.done + un.mt, 1u);
+        }
     }
 }
 
@@ -457,7 +465,7 @@ using namespace tsg;
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host);
 }
 
 extern "C" {
@@ -492,14 +500,14 @@ int tsg_profile_read(double *total_ms, int *launches) {
 
 int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                   long long ldy) {
-    return tcsc_gemm_peers(W, X, B, a, use_prelu, order, Y, M, N, K, ldy, 0, nullptr);
+    return tcsc_gemm_peers(W, X, B, a, use_prelu, order, Y, M, N, K, ldy, 0, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY) {
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host) {
     TSG_TRY(ensure_device());
     if (npeer < 0 || npeer > TSG_MAX_PEERS) return set_error(TSG_EINVAL, "too many peers");
     if (!W || !X || !B || !Y) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: null argument");
@@ -507,7 +515,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     if (order < 0 || order > 2) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
     if (ldy < N) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: ldy < N");
     if (M <= 0 || N <= 0) return TSG_OK;
-    const bool skinny = npeer == 0 && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
+    const bool skinny = npeer == 0 && !done && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
     if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
 
     TSG_TRY(build_kstream(W));
@@ -542,6 +550,13 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         }
     }
     p.units_total = p.units_full + R * p.sub;
+    p.done = done;
+    if (done_targets_host)  // arrivals each row tile will see: one per compute warp per unit covering it
+        for (int mt = 0; mt < p.mtiles; ++mt) {
+            unsigned int n = 0;
+            for (int nt = 0; nt < p.ntiles; ++nt) n += (mt * p.ntiles + nt < p.units_full) ? 1u : (unsigned int)p.sub;
+            done_targets_host[mt] = n * NWARP;
+        }
     int rc = launch_tiled(p, smem_bytes);
     int rc2 = dev_free(XT);
     return rc ? rc : rc2;

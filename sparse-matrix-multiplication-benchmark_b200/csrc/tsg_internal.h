@@ -97,7 +97,7 @@ int build_kstream(tsg_tcsc *W);
 int bcsr_build_cols(tsg_bcsr *W);
 // tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
 int transpose_x_tiles(const float *X, float *XT, int M, int K);
 }  // namespace tsg

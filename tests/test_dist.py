@@ -102,7 +102,7 @@ def _gpu_worker(rank, world, port_no, M, K, N, mode, q):
     W = t.DeviceTcsc.from_dense(t.gen_ternary_slice(K, N, c0, nc, 42, 1, 4))
     X = t.gen_uniform((M, K), 43) if rank == 0 else torch.zeros((M, K), device="cuda")
     B = t.gen_uniform((N,), 44)
-    Y = D.alloc_y(M, N) if mode == 1 else torch.empty((M, N), device="cuda")
+    Y = D.alloc_y(M, N) if mode >= 1 else torch.empty((M, N), device="cuda")
     for _ in range(2):  # twice: the second run overwrites a Y that peers have already read
         D.gemm(W, X, B, Y, N, a=0.2, use_prelu=True, root=0, mode=mode)
     torch.cuda.synchronize()
@@ -113,7 +113,7 @@ def _gpu_worker(rank, world, port_no, M, K, N, mode, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1], ids=["nccl_allgather", "fused_peer_stores"])
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["nccl_allgather", "fused_peer_stores", "copy_engine_overlap"])
 def test_two_gpus_bit_exact(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
