@@ -38,11 +38,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (M, K, N_per_gpu, num, den, description)
+    # name: (M, K, N, num, den, description); N is per GPU for "weak" workloads, total for "strong" ones
     "cfg2": (4096, 4096, 4096, 1, 10, "TCSC sparseGEMM+PReLU M=4096 K=4096 N=4096 90% sparsity (BASELINE.json configs[1])"),
     "cfg1": (64, 512, 512, 1, 2, "TCSC sparseGEMM+bias+PReLU M=64 K=512 N=512 50% sparsity (BASELINE.json configs[0])"),
     "cfg4": (8192, 4096, 14336, 1, 3, "ternary LLM-layer shape M=8192 K=4096 N=14336 66% sparsity (BASELINE.json configs[3])"),
+    "cfg5": (16384, 16384, 16384, 1, 10, "large sweep M=K=N=16384 90% sparsity, dense->TCSC conversion included in every step (BASELINE.json configs[4])"),
 }
+STRONG = {"cfg4", "cfg5"}       # total N fixed, columns split across the GPUs
+CONVERT_IN_STEP = {"cfg5"}      # the step re-converts the rank's dense slice (and rebuilds the gather stream) every time
 ALPHA = 0.2  # main.cpp:268
 SEED_W, SEED_X, SEED_B = 42, 43, 44
 METRIC = "sparse GEMM GFLOP/s-equiv (2*M*nnz + M*N per call, TCSC+bias+PReLU fp32)"
@@ -157,7 +160,7 @@ def run_reference(args):
     from oracle.pyoracle import Port
     port = Port()
     M, K, Ng, num, den, desc = WORKLOADS[args.workload]
-    N = Ng * max(1, args.gpus)
+    N = Ng if args.workload in STRONG else Ng * max(1, args.gpus)
     backend, kind, flags = cpu_reference_backend()
     pin_one_core()  # one thread pinned to one core, as benchmark.sh:36 does
     Wd = port.gen_ternary(K, N, SEED_W, num, den)
@@ -212,7 +215,8 @@ def run_ours(args):
     t.use_torch_stream()
 
     M, K, Ng, num, den, desc = WORKLOADS[args.workload]
-    N = Ng * world
+    strong = args.workload in STRONG
+    N = Ng if strong else Ng * world
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
 
     # ---- W: this rank's column slice, generated and converted on the device ----
@@ -239,7 +243,7 @@ def run_ours(args):
     nnz = int(nnz_t.item())
 
     # ---- inputs resident in HBM; rotate buffer sets so that each step streams from HBM, not L2 ----
-    nsets = 4 if (M * K + M * N) * 4 * 4 <= 8 << 30 else 2
+    nsets = 4 if (M * K + M * N) * 4 * 4 <= (8 << 30) else (2 if (M * K + M * N) * 4 * 2 <= (24 << 30) else 1)
     Xs = [t.gen_uniform((M, K), SEED_X + 100 * i) for i in range(nsets)]
     B = t.gen_uniform((N,), SEED_B)
     if world > 1 and args.dist_mode >= 1:
@@ -247,8 +251,15 @@ def run_ours(args):
     else:
         Ys = [torch.empty((M, N), device="cuda") for _ in range(nsets)]
 
+    convert_in_step = args.workload in CONVERT_IN_STEP
+    state = {"W": W}
+
     def step(i):
         X, Y = Xs[i % len(Xs)], Ys[i % len(Ys)]
+        if convert_in_step:  # configs[4]: dense -> TCSC (+ private gather stream) is part of the measured step
+            state["W"].destroy()
+            state["W"] = t.DeviceTcsc.from_dense(Wd)
+        W = state["W"]
         if world > 1:
             D.gemm(W, X, B, Y, N, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST, root=0, mode=args.dist_mode)
         else:
@@ -313,6 +324,7 @@ def run_ours(args):
     e2e = None
     cpu_baseline = None
     if world == 1:
+        W = state["W"]
         Wd_host = Wd.cpu().numpy()
         Wh = t.tcsc_from_dense(Wd_host)  # host tcsc_t + cached device mirror, as a reference caller would hold it
         Xh = [torch.empty((M, K), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -342,6 +354,7 @@ def run_ours(args):
             Xh.copy_(Xs[0].cpu())
         e2e_steps = max(3, min(args.steps, 10))
         Xd = torch.empty((M, K), device="cuda")
+        W = state["W"]
 
         def e2e_step():
             if rank == 0:
@@ -383,8 +396,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc if world == 1 else f"{desc}, per GPU: {world} x {Ng} = {N} columns N-sharded, X broadcast from rank 0, "
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc if world == 1 else f"{desc}, {'N=' + str(N) + ' columns split over ' + str(world) + ' GPUs' if strong else 'per GPU: ' + str(world) + ' x ' + str(Ng) + ' = ' + str(N) + ' columns'}, N-sharded, X broadcast from rank 0, "
                                                             f"Y all-gathered ({['ncclAllGather + re-layout', 'fused NVLink peer stores in the GEMM epilogue', 'copy-engine peer pushes gated by in-kernel progress counters, overlapped with the GEMM'][args.dist_mode]})",
                        "M": M, "K": K, "N": N, "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA,
                        "order": "tcsc_sgemm_prelu_basic (0, +pos asc, -neg asc, +b, PReLU) -- bit-identical to the reference",
@@ -407,6 +420,7 @@ def run_ours(args):
 
 
 def main():
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # the multi-GPU path blocks copy streams on stream-wait ops
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -123,6 +123,8 @@ void tsg_dist_partition(int N, int rank, int world, int *col0, int *ncols);
 /* fused mode needs a symmetric Y: every rank allocates `bytes` (cudaMalloc) and maps every peer's buffer through
  * CUDA IPC (handles exchanged over NCCL).  Collective; returns this rank's buffer, owned by D. */
 int tsg_dist_alloc_y(tsg_dist *D, size_t bytes, float **y_local);
+/* the peer mappings of the symmetric Y, indexed by rank (entry `rank` is the local buffer); up to 8 entries */
+int tsg_dist_peer_ptrs(tsg_dist *D, void *out[8]);
 /* stream-ordered cross-rank barrier (4-byte ncclAllReduce on the current stream) */
 int tsg_dist_barrier(tsg_dist *D);
 /* Y(M x N, full, on every rank) = [PReLU](X*W + B).  W_local holds this rank's column slice; B_dev is the full

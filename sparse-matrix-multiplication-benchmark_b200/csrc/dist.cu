@@ -14,6 +14,7 @@
 // library has no link-time NCCL dependency and loads on machines without it.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -209,6 +210,13 @@ int tsg_dist_alloc_y(tsg_dist *D, size_t bytes, float **y_local) {
     return TSG_OK;
 }
 
+// diagnostic: the peer mappings of the symmetric Y (entry `rank` is the local buffer)
+int tsg_dist_peer_ptrs(tsg_dist *D, void *out[TSG_MAX_PEERS]) {
+    if (!D) return set_error(TSG_EINVAL, "null handle");
+    for (int p = 0; p < TSG_MAX_PEERS; ++p) out[p] = D->y_peer[p];
+    return TSG_OK;
+}
+
 int tsg_dist_barrier(tsg_dist *D) {
     if (!D) return set_error(TSG_EINVAL, "null handle");
     if (D->world > 1) TSG_NCCL(g_nccl.AllReduce(D->flag, D->flag + 1, 1, ncclInt32, ncclSum, D->comm, stream()));
@@ -266,34 +274,64 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
                 TSG_CUDA(cudaEventCreateWithFlags(&D->ev_copy[p], cudaEventDisableTiming));
             }
         }
-        if (D->done_cap < mtiles) {
-            if (D->done) cudaFree(D->done);
-            TSG_CUDA(cudaMalloc(&D->done, sizeof(unsigned int) * mtiles));
-            D->done_cap = mtiles;
+        if (!D->done) {
+            TSG_CUDA(cudaMalloc(&D->done, sizeof(unsigned int) * 8));
+            D->done_cap = 8;
         }
-        std::vector<unsigned int> targets(mtiles, 0u);
-        TSG_CUDA(cudaMemsetAsync(D->done, 0, sizeof(unsigned int) * mtiles, st));
+        TSG_CUDA(cudaMemsetAsync(D->done, 0, sizeof(unsigned int) * 8, st));
         TSG_TRY(tsg_dist_barrier(D));  // peers have finished reading their previous Y
         TSG_CUDA(cudaEventRecord(D->ev_start, st));
+        Progress prog;
+        const bool trace = getenv("TSG_DIST_TRACE") != nullptr;  // diagnostic: when do the pushes run relative to the kernel?
+        cudaEvent_t tr_k0 = nullptr, tr_k1 = nullptr, tr_g[8] = {nullptr};
+        if (trace) {
+            cudaEventCreate(&tr_k0); cudaEventCreate(&tr_k1);
+            for (int g = 0; g < 8; ++g) cudaEventCreate(&tr_g[g]);
+            cudaEventRecord(tr_k0, st);
+        }
         if (ncols > 0)
-            TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 0, nullptr, D->done, targets.data()));
-        const int group = 4;  // row tiles per copy: 512 rows x ncols floats
-        for (int p = 1; p < D->world && ncols > 0; ++p) {
-            const int q = (D->rank + p) % D->world;
-            cudaStream_t cs = D->copy_stream[q];
-            TSG_CUDA(cudaStreamWaitEvent(cs, D->ev_start, 0));
-            for (int g0 = 0; g0 < mtiles; g0 += group) {
-                const int g1 = (g0 + group < mtiles) ? g0 + group : mtiles;
-                for (int mt = g0; mt < g1; ++mt) {
-                    int rc = D->wait_value(cs, (unsigned long long)(uintptr_t)(D->done + mt), targets[mt], /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
+            TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 0, nullptr, D->done, &prog));
+        if (trace) cudaEventRecord(tr_k1, st);
+        (void)mtiles;
+        // A FEW copy streams (peers dealt round-robin): one stream tops out near 350 GB/s when all ranks push at once,
+        // while one stream per peer makes the blocking stream-wait memory ops alias onto the same hardware queues and
+        // serialise behind one another (both measured at 8 GPUs); TSG_DIST_COPY_STREAMS overrides the default of 2.
+        if (ncols > 0) {
+            int ncs = 2;
+            if (const char *e = getenv("TSG_DIST_COPY_STREAMS")) ncs = atoi(e);
+            if (ncs < 1) ncs = 1;
+            if (ncs > D->world - 1) ncs = D->world - 1;
+            for (int c = 0; c < ncs; ++c) {
+                cudaStream_t cs = D->copy_stream[c];
+                TSG_CUDA(cudaStreamWaitEvent(cs, D->ev_start, 0));
+                for (int g = 0; g < prog.ngroups; ++g) {
+                    int rc = D->wait_value(cs, (unsigned long long)(uintptr_t)(D->done + g), prog.target[g], /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
                     if (rc != 0) return set_error(TSG_ECUDA, "cuStreamWaitValue32 failed (%d)", rc);
+                    const int r0 = prog.gbound[g] * 128, r1 = (prog.gbound[g + 1] * 128 < M) ? prog.gbound[g + 1] * 128 : M;
+                    for (int p = 1 + c; p < D->world; p += ncs) {
+                        const int q = (D->rank + p) % D->world;  // start with the next rank: the ranks do not all hit one peer at once
+                        TSG_CUDA(cudaMemcpy2DAsync(D->y_peer[q] + (size_t)r0 * N + col0, (size_t)N * 4, Y + (size_t)r0 * N + col0,
+                                                   (size_t)N * 4, (size_t)ncols * 4, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, cs));
+                    }
+                    if (trace && c == 0) cudaEventRecord(tr_g[g], cs);
                 }
-                const int r0 = g0 * 128, r1 = (g1 * 128 < M) ? g1 * 128 : M;
-                TSG_CUDA(cudaMemcpy2DAsync(D->y_peer[q] + (size_t)r0 * N + col0, (size_t)N * 4, Y + (size_t)r0 * N + col0, (size_t)N * 4,
-                                           (size_t)ncols * 4, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, cs));
+                TSG_CUDA(cudaEventRecord(D->ev_copy[c], cs));
+                TSG_CUDA(cudaStreamWaitEvent(st, D->ev_copy[c], 0));
             }
-            TSG_CUDA(cudaEventRecord(D->ev_copy[q], cs));
-            TSG_CUDA(cudaStreamWaitEvent(st, D->ev_copy[q], 0));
+        }
+        if (trace) {
+            cudaStreamSynchronize(st);
+            float tk = 0.f;
+            cudaEventElapsedTime(&tk, tr_k0, tr_k1);
+            fprintf(stderr, "[tsg_dist trace rank %d] transpose+kernel %.3f ms; pushes of group done at:", D->rank, tk);
+            for (int g = 0; g < prog.ngroups; ++g) {
+                float tg = 0.f;
+                cudaEventElapsedTime(&tg, tr_k0, tr_g[g]);
+                fprintf(stderr, " g%d(rows %d..%d)=%.3f", g, prog.gbound[g] * 128, prog.gbound[g + 1] * 128, tg);
+            }
+            fprintf(stderr, " ms\n");
+            cudaEventDestroy(tr_k0); cudaEventDestroy(tr_k1);
+            for (int g = 0; g < 8; ++g) cudaEventDestroy(tr_g[g]);
         }
         return tsg_dist_barrier(D);  // every rank's pushes have completed => every Y is whole
     }

@@ -57,6 +57,8 @@ struct GemmParams {
     // progress counters, one per 128-row tile: every compute warp bumps done[mt] once its part of a unit is stored, so
     // that stream-ordered peer copies (dist.cu, mode 2) can start on finished row blocks while the kernel still runs
     unsigned int *done;
+    int ngroups;       // row tiles [gbound[g], gbound[g+1]) form progress group g (at most 8 groups)
+    int gbound[9];
 };
 
 // ---- PTX helpers ----------------------------------------------------------------------------------------------------
@@ -299,7 +301,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         if (p.done) {  // publish: this warp's share of unit (mt, n0) is in memory
             __threadfence_system();
             __syncwarp();
-            if (lane == 0) atomicAdd(p.done + un.mt, 1u);
+            if (lane == 0) {
+                int g = 0;
+                while (g + 1 < p.ngroups && un.mt >= p.gbound[g + 1]) ++g;
+                atomicAdd(p.done + g, 1u);
+            }
         }
     }
 }
@@ -355,23 +361,38 @@ __global__ void k_skinny_pack_x(const float *__restrict__ X, float *__restrict__
 }
 
 template <int MT>
+__device__ __forceinline__ void skinny_add(float (&acc)[MT], const float *__restrict__ px, float sign) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(px));
+    acc[0] += sign * a.x;
+    if (MT > 1) acc[1 % MT] += sign * a.y;
+    if (MT > 2) { acc[2 % MT] += sign * a.z; acc[3 % MT] += sign * a.w; }
+    if (MT > 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(px) + 1);
+        acc[4 % MT] += sign * b.x; acc[5 % MT] += sign * b.y; acc[6 % MT] += sign * b.z; acc[7 % MT] += sign * b.w;
+    }
+}
+
+// lanes stride over the list; four independent index loads, then four independent gathers per trip (the list is short:
+// latency, not bandwidth, is what a warp sees, so keep several loads in flight)
+template <int MT>
 __device__ __forceinline__ void skinny_accumulate(float (&acc)[MT], const float *__restrict__ xs, const int *__restrict__ idx, int lo,
                                                   int hi, int lane, float sign) {
-    for (int t = lo + lane; t < hi; t += 32) {
-        const int k = __ldg(idx + t);
-        const float *px = xs + (size_t)k * SK_MT;
-        if (MT <= 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(px));
-            acc[0] += sign * a.x;
-            if (MT > 1) acc[1 % MT] += sign * a.y;
-            if (MT > 2) { acc[2 % MT] += sign * a.z; acc[3 % MT] += sign * a.w; }
-        } else {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(px));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(px) + 1);
-            acc[0] += sign * a.x; acc[1 % MT] += sign * a.y; acc[2 % MT] += sign * a.z; acc[3 % MT] += sign * a.w;
-            acc[4 % MT] += sign * b.x; acc[5 % MT] += sign * b.y; acc[6 % MT] += sign * b.z; acc[7 % MT] += sign * b.w;
-        }
+    int t = lo + lane;
+    for (; t + 96 < hi; t += 128) {
+        const int k0 = __ldg(idx + t), k1 = __ldg(idx + t + 32), k2 = __ldg(idx + t + 64), k3 = __ldg(idx + t + 96);
+        skinny_add<MT>(acc, xs + (size_t)k0 * SK_MT, sign);
+        skinny_add<MT>(acc, xs + (size_t)k1 * SK_MT, sign);
+        skinny_add<MT>(acc, xs + (size_t)k2 * SK_MT, sign);
+        skinny_add<MT>(acc, xs + (size_t)k3 * SK_MT, sign);
     }
+    int kk[3];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (t + 32 * i < hi) { kk[i] = __ldg(idx + t + 32 * i); n = i + 1; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (i < n) skinny_add<MT>(acc, xs + (size_t)kk[i] * SK_MT, sign);
 }
 
 template <int MT>
@@ -465,7 +486,7 @@ using namespace tsg;
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog);
 }
 
 extern "C" {
@@ -507,7 +528,7 @@ int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host) {
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog) {
     TSG_TRY(ensure_device());
     if (npeer < 0 || npeer > TSG_MAX_PEERS) return set_error(TSG_EINVAL, "too many peers");
     if (!W || !X || !B || !Y) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: null argument");
@@ -551,12 +572,32 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     }
     p.units_total = p.units_full + R * p.sub;
     p.done = done;
-    if (done_targets_host)  // arrivals each row tile will see: one per compute warp per unit covering it
-        for (int mt = 0; mt < p.mtiles; ++mt) {
-            unsigned int n = 0;
-            for (int nt = 0; nt < p.ntiles; ++nt) n += (mt * p.ntiles + nt < p.units_full) ? 1u : (unsigned int)p.sub;
-            done_targets_host[mt] = n * NWARP;
+    p.ngroups = 0;
+    for (int g = 0; g < 9; ++g) p.gbound[g] = 0;
+    if (done && prog) {
+        // progress groups: three quarters of the row tiles in three big groups (they complete round by round of the
+        // persistent grid anyway), then ever smaller ones so that little is left to push once the kernel retires
+        const double frac[8] = {0.25, 0.25, 0.25, 0.125, 0.0625, 0.03125, 0.015625, 1.0};
+        int b = 0, g = 0;
+        p.gbound[0] = 0;
+        while (b < p.mtiles && g < 8) {
+            int sz = (g == 7) ? p.mtiles - b : (int)(p.mtiles * frac[g] + 0.5);
+            if (sz < 1) sz = 1;
+            if (b + sz > p.mtiles) sz = p.mtiles - b;
+            b += sz;
+            p.gbound[++g] = b;
         }
+        if (b < p.mtiles) p.gbound[g] = p.mtiles;
+        p.ngroups = g;
+        prog->ngroups = g;
+        for (int i = 0; i <= g; ++i) prog->gbound[i] = p.gbound[i];
+        for (int i = 0; i < g; ++i) {  // arrivals group i will see: one per compute warp per unit covering its row tiles
+            unsigned int n = 0;
+            for (int mt = p.gbound[i]; mt < p.gbound[i + 1]; ++mt)
+                for (int nt = 0; nt < p.ntiles; ++nt) n += (mt * p.ntiles + nt < p.units_full) ? 1u : (unsigned int)p.sub;
+            prog->target[i] = n * NWARP;
+        }
+    }
     int rc = launch_tiled(p, smem_bytes);
     int rc2 = dev_free(XT);
     return rc ? rc : rc2;

@@ -95,9 +95,15 @@ int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t 
 int is_device_pointer(const void *p);
 int build_kstream(tsg_tcsc *W);
 int bcsr_build_cols(tsg_bcsr *W);
+// progress groups of the tiled kernel (dist.cu mode 2): row tiles [gbound[g], gbound[g+1]) are complete when done[g] == target[g]
+struct Progress {
+    int ngroups = 0;
+    int gbound[9] = {0};
+    unsigned int target[8] = {0};
+};
 // tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, unsigned int *done_targets_host);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
 int transpose_x_tiles(const float *X, float *XT, int M, int K);
 }  // namespace tsg
