@@ -73,7 +73,7 @@ int tsg_sparse_gemm_f32(const float *X, const int *col_start_pos, const int *col
     if (M <= 0 || N <= 0) return TSG_OK;
     tsg_tcsc *dev = raw_mirror(col_start_pos, col_start_neg, row_index_pos, row_index_neg, N, K);
     if (!dev) return TSG_ECUDA;
-    if (!tsg_shim_is_device(X) && !tsg_shim_is_device(Y))
+    if (!tsg_shim_is_device(X) && !tsg_shim_is_device(Y) && (size_t)M * ((size_t)K + (size_t)N) * 4 >= ((size_t)8 << 20))
         return tsg_shim_tcsc_gemm_hostpipe(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
     void *dX = nullptr, *dB = nullptr, *dY = nullptr;
     int ox = 0, ob = 0, oy = 0, rc;

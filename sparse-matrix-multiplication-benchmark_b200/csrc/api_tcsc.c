@@ -135,7 +135,8 @@ static void run_gemm(const float *X, const tcsc_t *W, const float *B, float a, i
     tsg_tcsc *dev = mirror_of(W);
     if (!dev) return; /* reason in sparse_last_error() */
     const int x_dev = tsg_shim_is_device(X), y_dev = tsg_shim_is_device(Y);
-    if (!x_dev && !y_dev) { /* the reference's calling convention: everything in host memory */
+    if (!x_dev && !y_dev && (size_t)M * ((size_t)K + (size_t)N) * sizeof(float) >= ((size_t)8 << 20)) {
+        /* the reference's calling convention, everything in host memory, and enough of it to be worth pipelining */
         tsg_shim_tcsc_gemm_hostpipe(dev, X, B, a, use_prelu, order, Y, M, N, K);
         return;
     }

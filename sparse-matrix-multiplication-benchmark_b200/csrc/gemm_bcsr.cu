@@ -118,7 +118,7 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
     if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) {
         const int mtiles = (M + 127) / 128;
         float *XT = nullptr;
-        TSG_TRY(dev_alloc_t(&XT, (size_t)mtiles * K * 128));
+        TSG_TRY(ws_acquire(0, (size_t)mtiles * K * 128 * sizeof(float), reinterpret_cast<void **>(&XT)));
         TSG_TRY(transpose_x_tiles(X, XT, M, K));
         int gx = (bc + 7) / 8;
         const int cap = (num_sms() * 8 + mtiles - 1) / mtiles;
@@ -134,7 +134,7 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
         }
 #undef TSG_BCSR_LAUNCH
         TSG_KERNEL_CHECK("k_bcsr_gemm");
-        return dev_free(XT);
+        return ws_release(0);
     }
     const long long total = (long long)M * ncov;
     // generic path writes columns [0, ncov): reuse the element kernel with N restricted via ldy addressing

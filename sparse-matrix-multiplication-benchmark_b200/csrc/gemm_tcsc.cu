@@ -395,6 +395,46 @@ __device__ __forceinline__ void skinny_accumulate(float (&acc)[MT], const float 
         if (i < n) skinny_add<MT>(acc, xs + (size_t)kk[i] * SK_MT, sign);
 }
 
+// M <= 2: no repacking, gather straight from the row-major X (one row = one K-vector)
+__global__ void __launch_bounds__(256) k_tcsc_skinny_direct(const float *__restrict__ X, const int *__restrict__ csp, const int *__restrict__ csn,
+                                                            const int *__restrict__ rip, const int *__restrict__ rin, const float *__restrict__ B,
+                                                            float a, int use_prelu, float *__restrict__ Y, long long ldy, int M, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float *x1 = X + (M > 1 ? (size_t)K : 0);
+    for (int n = wglobal; n < N; n += nwarps) {
+        float a0 = 0.f, a1 = 0.f;
+        const int p0 = __ldg(csp + n), p1 = __ldg(csp + n + 1), q0 = __ldg(csn + n), q1 = __ldg(csn + n + 1);
+        for (int t = p0 + lane; t < p1; t += 32) {
+            const int k = __ldg(rip + t);
+            a0 += __ldg(X + k);
+            a1 += __ldg(x1 + k);
+        }
+        for (int t = q0 + lane; t < q1; t += 32) {
+            const int k = __ldg(rin + t);
+            a0 -= __ldg(X + k);
+            a1 -= __ldg(x1 + k);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, d);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+        }
+        if (lane == 0) {
+            const float b = __ldg(B + n);
+            float y = a0 + b;
+            if (use_prelu) y = (y < 0.0f) ? a * y : y;
+            Y[n] = y;
+            if (M > 1) {
+                y = a1 + b;
+                if (use_prelu) y = (y < 0.0f) ? a * y : y;
+                Y[(size_t)ldy + n] = y;
+            }
+        }
+    }
+}
+
 template <int MT>
 __global__ void __launch_bounds__(256) k_tcsc_skinny(const float *__restrict__ XS, const int *__restrict__ csp, const int *__restrict__ csn,
                                                      const int *__restrict__ rip, const int *__restrict__ rin, const float *__restrict__ B,
@@ -437,15 +477,20 @@ static thread_local std::vector<cudaEvent_t> g_prof_events;
 static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy) {
     cudaStream_t st = stream();
     const int groups = (M + SK_MT - 1) / SK_MT;
-    float *XS = nullptr;
-    TSG_TRY(dev_alloc_t(&XS, (size_t)groups * K * SK_MT));
-    k_skinny_pack_x<<<dim3((K + 255) / 256, groups), 256, 0, st>>>(X, XS, M, K);
-    TSG_KERNEL_CHECK("k_skinny_pack_x");
     const int warps_per_cta = 8;
     int ctas = (N + warps_per_cta - 1) / warps_per_cta;
     const int max_ctas = num_sms() * 8;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
+    if (M <= 2) {
+        k_tcsc_skinny_direct<<<ctas, 256, 0, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K);
+        TSG_KERNEL_CHECK("k_tcsc_skinny_direct");
+        return TSG_OK;
+    }
+    float *XS = nullptr;
+    TSG_TRY(ws_acquire(1, (size_t)groups * K * SK_MT * sizeof(float), reinterpret_cast<void **>(&XS)));
+    k_skinny_pack_x<<<dim3((K + 255) / 256, groups), 256, 0, st>>>(X, XS, M, K);
+    TSG_KERNEL_CHECK("k_skinny_pack_x");
     dim3 grid(ctas, groups);
     const int mt = (M >= 5) ? 8 : (M >= 3 ? 4 : (M == 2 ? 2 : 1));
     switch (mt) {
@@ -455,7 +500,7 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
         default: k_tcsc_skinny<8><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
     }
     TSG_KERNEL_CHECK("k_tcsc_skinny");
-    return dev_free(XS);
+    return ws_release(1);
 }
 
 static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
@@ -544,7 +589,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     GemmParams p;
     p.mtiles = (M + TM - 1) / TM;
     float *XT = nullptr;
-    TSG_TRY(dev_alloc_t(&XT, (size_t)p.mtiles * (K > 0 ? K : 1) * TM));
+    TSG_TRY(ws_acquire(0, (size_t)p.mtiles * (K > 0 ? K : 1) * TM * sizeof(float), reinterpret_cast<void **>(&XT)));
     if (K > 0) TSG_TRY(transpose_x_tiles(X, XT, M, K));
     p.XT = XT; p.cnt = ks.cnt; p.woff = ks.woff; p.body = ks.body; p.B = B; p.Y = Y; p.ldy = ldy;
     p.M = M; p.N = N; p.K = K; p.kc = ks.kc; p.nchunk = (K > 0) ? ks.nchunk : 0; p.ncols_pad = ks.ncols_pad; p.ngroup = ks.ngroup;
@@ -599,7 +644,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         }
     }
     int rc = launch_tiled(p, smem_bytes);
-    int rc2 = dev_free(XT);
+    int rc2 = ws_release(0);
     return rc ? rc : rc2;
 }
 }  // namespace tsg

@@ -73,6 +73,42 @@ int dev_alloc(void **out, size_t bytes) {
     return TSG_OK;
 }
 
+// ---- per-thread workspaces that survive across calls (XT / XS): no cudaMallocAsync + cudaFreeAsync per GEMM ------------
+static thread_local Workspace g_ws[2];
+
+int ws_acquire(int slot, size_t bytes, void **out) {
+    Workspace &w = g_ws[slot];
+    if (bytes == 0) bytes = 16;
+    if (!w.ev) {
+        if (cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming) != cudaSuccess) return set_error(TSG_ECUDA, "cudaEventCreate failed");
+    }
+    if (w.used && w.last != g_stream) {  // the previous user ran on another stream: order this one behind it
+        if (cudaStreamWaitEvent(g_stream, w.ev, 0) != cudaSuccess) return set_error(TSG_ECUDA, "cudaStreamWaitEvent failed");
+    }
+    if (w.cap < bytes) {
+        if (w.p) cudaFreeAsync(w.p, g_stream);
+        w.p = nullptr;
+        w.cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMallocAsync(&w.p, want, g_stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(TSG_ENOMEM, "cudaMallocAsync(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        w.cap = want;
+    }
+    *out = w.p;
+    return TSG_OK;
+}
+
+int ws_release(int slot) {
+    Workspace &w = g_ws[slot];
+    w.last = g_stream;
+    w.used = true;
+    if (cudaEventRecord(w.ev, g_stream) != cudaSuccess) return set_error(TSG_ECUDA, "cudaEventRecord failed");
+    return TSG_OK;
+}
+
 int dev_free(void *p) {
     if (!p) return TSG_OK;
     cudaError_t e = cudaFreeAsync(p, g_stream);

@@ -47,6 +47,17 @@ int ensure_device();  // TSG_OK iff a usable sm_100 device is current (cached)
 
 int dev_alloc(void **out, size_t bytes);
 int dev_free(void *p);
+// workspace that persists across calls on this thread (slot 0: XT tiles, slot 1: skinny X pack); stream-safe: a
+// user on another stream is ordered behind the previous one with an event
+struct Workspace {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaStream_t last = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool used = false;
+};
+int ws_acquire(int slot, size_t bytes, void **out);
+int ws_release(int slot);
 template <typename T>
 inline int dev_alloc_t(T **out, size_t count) {
     return dev_alloc(reinterpret_cast<void **>(out), count * sizeof(T));
