@@ -99,7 +99,7 @@ template <bool NEG>
 __device__ __forceinline__ void gather_word(float2 &a01, float2 &a23, uint32_t word, uint32_t xbase) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const uint32_t k = (word >> (8 * e)) & 0xFFu;
+        const uint32_t k = __byte_perm(word, 0u, 0x4440u + e);  // byte e, zero-extended (one PRMT)
         if (k != 0xFFu) {  // warp-uniform: compiles to predicated LDS.128 + FADD2, no branch
             float4 x;  // 32-bit shared-window address: no generic->shared conversion per load
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(k * (TM * 4) + xbase));
@@ -130,12 +130,16 @@ __device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t x
 #pragma unroll
     for (int i = 0; i < CWMAX / 4; ++i) cwd[i] = (4 * i < cw) ? *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i) : 0u;
     const uint4 *qp = reinterpret_cast<const uint4 *>(body_s + off);  // every list starts on a 16-byte boundary
+    // one quad of look-ahead: the lists of a warp are contiguous in the stream, so the next quad is fetched while the
+    // current one is being gathered (reading one quad past the warp's region stays inside the stage buffer)
+    uint4 nxt = *qp;
 #pragma unroll
     for (int j = 0; j < CWMAX; ++j) {
         const int nq = (cwd[j >> 2] >> (8 * (j & 3))) & 0xFF;  // 0 for j >= cw
 #pragma unroll 1
         for (int i = 0; i < nq; ++i) {
-            const uint4 w = *qp++;  // one uniform-address LDS.128 = up to 16 non-zeros
+            const uint4 w = nxt;  // one uniform-address LDS.128 = up to 16 non-zeros
+            nxt = *++qp;
             gather_word<NEG>(acc[j][0], acc[j][1], w.x, xbase);
             if (w.y != 0xFFFFFFFFu) {  // entries are packed from the front: an all-padding word ends the list
                 gather_word<NEG>(acc[j][0], acc[j][1], w.y, xbase);

@@ -56,9 +56,11 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
         TSG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     }
     TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
-    // slabs: multiples of 128 rows (the kernel's row tile), about 1024 rows each, at least 4 when M allows, balanced so
-    // that no tiny tail slab is left over
-    int nslab = (M + 1023) / 1024;
+    // slabs: multiples of 128 rows (the kernel's row tile).  PCIe is the bottleneck of a host-pointer call, so the slabs
+    // are kept small (about 512 rows, at most 16 of them): the un-overlapped head (first H2D) and tail (last kernel +
+    // last D2H) shrink with the slab, and the kernel's lower efficiency on small slabs hides under the copies
+    int nslab = (M + 511) / 512;
+    if (nslab > 16) nslab = 16;
     if (nslab < 4) nslab = (M + 127) / 128 < 4 ? (M + 127) / 128 : 4;
     int slab = (((M + nslab - 1) / nslab) + 127) / 128 * 128;
     if (M < TSG_SKINNY_M) slab = M;

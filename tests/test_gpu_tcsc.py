@@ -270,3 +270,42 @@ def test_full_size_cfg2(t, port):
     assert torch.equal(Y2, Y1 * 4.0)
     w.gemm(-X, Z0, Y2)               # negation too
     assert torch.equal(Y2, -Y1)
+
+
+def test_deterministic_and_kernel_families_agree(t, port):
+    """Same call twice => same bits (the persistent grid's schedule never changes a column's summation order); the
+    skinny and the tiled kernel agree to the tolerance on the same input."""
+    import torch
+    M, K, N = 96, 2048, 1536
+    Wd = t.gen_ternary(K, N, 90, 1, 10)
+    w = t.DeviceTcsc.from_dense(Wd)
+    X, B = t.gen_uniform((M, K), 91), t.gen_uniform((N,), 92)
+    Y1, Y2, Y3 = (torch.empty((M, N), device="cuda") for _ in range(3))
+    w.gemm(X, B, Y1, a=0.2, use_prelu=True)
+    w.gemm(X, B, Y2, a=0.2, use_prelu=True)
+    assert torch.equal(Y1, Y2)
+    t.lib().tsg_tcsc_set_kernel(2)
+    try:
+        w.gemm(X, B, Y3, a=0.2, use_prelu=True)
+    finally:
+        t.lib().tsg_tcsc_set_kernel(0)
+    denom = torch.clamp(Y1.abs(), min=1.0)
+    assert float(((Y1 - Y3).abs() / denom).max()) <= 2e-5
+    # column slab written into a wider Y (ldy > N): neighbours untouched
+    Ywide = torch.full((M, N + 64), -7.0, device="cuda")
+    t.lib().tsg_tcsc_gemm(w.h, t._ptr(X), t._ptr(B), 0.2, 1, 1, Ywide.data_ptr() + 4 * 32, M, N, K, N + 64)
+    torch.cuda.synchronize()
+    assert torch.equal(Ywide[:, 32:32 + N], Y1) and bool((Ywide[:, :32] == -7).all()) and bool((Ywide[:, 32 + N:] == -7).all())
+
+
+def test_host_pointer_pipeline_large(t, port):
+    """Host-pointer call big enough for the H2D / kernel / D2H slab pipeline (>= 8 MB), ragged M."""
+    M, K, N = 1100, 1024, 1024
+    Wd = port.gen_ternary(K, N, 95, 1, 10)
+    w, wo = t.tcsc_from_dense(Wd), port.tcsc_from_dense(Wd)
+    X, B = port.gen_uniform((M, K), 96), port.gen_uniform((N,), 97)
+    y = t.tcsc_sgemm_prelu_basic(X, w, B, 0.2)
+    assert np.array_equal(y, port.tcsc_sgemm_prelu_basic(X, wo, B, 0.2))
+    y = t.tcsc_sgemm_optimized(X, w, B)
+    assert np.array_equal(y, port.tcsc_sgemm_optimized(X, wo, B))
+    w.free()
