@@ -35,18 +35,60 @@ __global__ void __launch_bounds__(256) k_bcsr_gemm(const float *__restrict__ XT,
             acc[j][0] = b; acc[j][1] = b; acc[j][2] = b; acc[j][3] = b;
         }
         const int e0 = __ldg(cptr + col), e1 = __ldg(cptr + col + 1);
-        for (int e = e0; e < e1; ++e) {
-            const int brow = __ldg(crow + e);
-            const float *blk = values + (size_t)__ldg(cblk + e) * r * C;
-            for (int i = 0; i < r; ++i) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(xt + (size_t)(brow * r + i) * 128));
+        if (r == 1) {
+            // one-row blocks (the blocking the reference tests, test_bcsr.cpp:16-17): batches of four blocks with all
+            // loads issued before the first FMA, so four X rows and four value rows are in flight per warp
+            int e = e0;
+            for (; e + 4 <= e1; e += 4) {
+                int br4[4], bk4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { br4[u] = __ldg(crow + e + u); bk4[u] = __ldg(cblk + e + u); }
+                float4 x4[4];
+                float w4[4][C];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    x4[u] = __ldg(reinterpret_cast<const float4 *>(xt + (size_t)br4[u] * 128));
+                    const float *blk = values + (size_t)bk4[u] * C;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) w4[u][j] = __ldg(blk + j);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {  // ascending block-row = ascending k, as bcsr.c:152-170 accumulates
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        acc[j][0] = fmaf(x4[u].x, w4[u][j], acc[j][0]);
+                        acc[j][1] = fmaf(x4[u].y, w4[u][j], acc[j][1]);
+                        acc[j][2] = fmaf(x4[u].z, w4[u][j], acc[j][2]);
+                        acc[j][3] = fmaf(x4[u].w, w4[u][j], acc[j][3]);
+                    }
+                }
+            }
+            for (; e < e1; ++e) {
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(xt + (size_t)__ldg(crow + e) * 128));
+                const float *blk = values + (size_t)__ldg(cblk + e) * C;
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
-                    const float w = __ldg(blk + i * C + j);
+                    const float w = __ldg(blk + j);
                     acc[j][0] = fmaf(x.x, w, acc[j][0]);
                     acc[j][1] = fmaf(x.y, w, acc[j][1]);
                     acc[j][2] = fmaf(x.z, w, acc[j][2]);
                     acc[j][3] = fmaf(x.w, w, acc[j][3]);
+                }
+            }
+        } else {
+            for (int e = e0; e < e1; ++e) {
+                const int brow = __ldg(crow + e);
+                const float *blk = values + (size_t)__ldg(cblk + e) * r * C;
+                for (int i = 0; i < r; ++i) {
+                    const float4 x = __ldg(reinterpret_cast<const float4 *>(xt + (size_t)(brow * r + i) * 128));
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        const float w = __ldg(blk + i * C + j);
+                        acc[j][0] = fmaf(x.x, w, acc[j][0]);
+                        acc[j][1] = fmaf(x.y, w, acc[j][1]);
+                        acc[j][2] = fmaf(x.z, w, acc[j][2]);
+                        acc[j][3] = fmaf(x.w, w, acc[j][3]);
+                    }
                 }
             }
         }
