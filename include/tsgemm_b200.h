@@ -125,6 +125,10 @@ void tsg_dist_partition(int N, int rank, int world, int *col0, int *ncols);
 int tsg_dist_alloc_y(tsg_dist *D, size_t bytes, float **y_local);
 /* the peer mappings of the symmetric Y, indexed by rank (entry `rank` is the local buffer); up to 8 entries */
 int tsg_dist_peer_ptrs(tsg_dist *D, void *out[8]);
+/* diagnostic (tools/peer_store_bw.py): write a rows x cols tile pattern into dst (row pitch ld floats; may be a peer
+ * mapping) `iters` times; mode 0 = per-lane 64-byte row segments (the fused epilogue's pattern), mode 1 = 1 KB row
+ * segments from shared memory with bulk async (TMA) stores */
+int tsg_dbg_peer_store(float *dst, long long ld, int rows, int cols, int iters, int mode);
 /* stream-ordered cross-rank barrier (4-byte ncclAllReduce on the current stream) */
 int tsg_dist_barrier(tsg_dist *D);
 /* Y(M x N, full, on every rank) = [PReLU](X*W + B).  W_local holds this rank's column slice; B_dev is the full
@@ -134,7 +138,10 @@ int tsg_dist_barrier(tsg_dist *D);
  *         the local Y and straight into every peer's Y over NVLink (fused all-gather).
  * mode 2: Y_dev must be the tsg_dist_alloc_y buffer; the kernel writes the local slab and bumps a progress counter
  *         per 128-row tile; per peer a copy stream waits on those counters (cuStreamWaitValue32, no SM involved) and
- *         pushes finished row blocks with strided 2-D DMA copies, so the all-gather overlaps the GEMM (M >= 32). */
+ *         pushes finished row blocks with strided 2-D DMA copies, so the all-gather overlaps the GEMM (M >= 32).
+ * mode 3: Y_dev must be the tsg_dist_alloc_y buffer; fused all-gather through the TMA engine: every finished 128-row
+ *         tile is staged in shared memory and its row segments are written to the local Y and to every peer's Y with
+ *         bulk async stores while the SMs gather the next tile (M >= 32, N and the slab width multiples of 4). */
 int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X_dev, int root, const float *B_dev, float a, int use_prelu,
                   int order, float *Y_dev, int M, int N, int K, int mode);
 

@@ -253,6 +253,22 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         return tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
     }
 
+    if (mode == 3) {
+        // (2+3 fused, TMA) the kernel stages every finished 128-row tile in shared memory and the TMA engine writes each
+        // row segment (up to 1 KB) to the local Y and to every peer's Y with bulk async stores: NVLink-sized packets
+        // (687 GB/s measured, tools/peer_store_bw.py, vs 145 GB/s for mode 1's per-lane stores), issued while the SMs
+        // are already gathering the next tile.
+        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3): Y must be the buffer returned by tsg_dist_alloc_y");
+        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3): Y buffer too small");
+        if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 3) needs M >= %d", TSG_SKINNY_M);
+        float *peers[TSG_MAX_PEERS];
+        int np = 0;
+        for (int p = 1; p < D->world; ++p) peers[np++] = D->y_peer[(D->rank + p) % D->world] + col0;
+        TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y
+        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr, 1));
+        return tsg_dist_barrier(D);
+    }
+
     if (mode == 2) {
         // (2) one persistent kernel writes the local slab and bumps a progress counter per 128-row tile;
         // (3) per peer, a copy stream waits (stream memory op, no SM involved) until a block of row tiles is complete
@@ -355,3 +371,71 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// diagnostic: how fast can SMs write a row-major tile into a PEER's memory over NVLink?
+//   mode 0  the access pattern of mode 1's epilogue: every lane stores 64 contiguous bytes of a different row (4 x st.v4)
+//   mode 1  whole 1 KB row segments staged in shared memory and written with bulk async stores (TMA engine, UBLKCP)
+// Used by tools/peer_store_bw.py; informs the design of a fused all-gather epilogue.
+// =====================================================================================================================
+namespace tsg {
+
+__global__ void __launch_bounds__(512) k_peer_store_scattered(float *__restrict__ dst, long long ld, int rows, int cols, int iters) {
+    // CTA b owns row tile (b % mt), column tile (b / mt); 16 warps x 16 columns, lane l rows 4l..4l+3 (as k_tcsc_gemm)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mtiles = rows / 128, ntiles = cols / 256;
+    for (int it = 0; it < iters; ++it)
+        for (int u = blockIdx.x; u < mtiles * ntiles; u += gridDim.x) {
+            const int mt = u / ntiles, nt = u % ntiles;
+            const float4 v = make_float4((float)u, (float)lane, (float)warp, (float)it);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float *row = dst + (size_t)(mt * 128 + lane * 4 + r) * ld + nt * 256 + warp * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(row + j) = v;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(512) k_peer_store_bulk(float *__restrict__ dst, long long ld, int rows, int cols, int iters) {
+    extern __shared__ __align__(128) float tile[];  // [128][256] floats = 128 KB
+    const int mtiles = rows / 128, ntiles = cols / 256;
+    for (int i = threadIdx.x; i < 128 * 256; i += blockDim.x) tile[i] = (float)i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    for (int it = 0; it < iters; ++it)
+        for (int u = blockIdx.x; u < mtiles * ntiles; u += gridDim.x) {
+            const int mt = u / ntiles, nt = u % ntiles;
+            if (threadIdx.x < 128) {  // one bulk store of a 1 KB row segment per thread
+                const int r = threadIdx.x;
+                float *row = dst + (size_t)(mt * 128 + r) * ld + nt * 256;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row),
+                             "r"((uint32_t)__cvta_generic_to_shared(tile + r * 256)), "r"(1024)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x < 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace tsg
+
+extern "C" int tsg_dbg_peer_store(float *dst, long long ld, int rows, int cols, int iters, int mode) {
+    TSG_TRY(ensure_device());
+    if (rows % 128 || cols % 256) return set_error(TSG_EINVAL, "rows %% 128 and cols %% 256 must be 0");
+    const int grid = num_sms();
+    if (mode == 0) {
+        k_peer_store_scattered<<<grid, 512, 0, stream()>>>(dst, ld, rows, cols, iters);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            TSG_CUDA(cudaFuncSetAttribute(k_peer_store_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 256 * 4));
+            attr = true;
+        }
+        k_peer_store_bulk<<<grid, 512, 128 * 256 * 4, stream()>>>(dst, ld, rows, cols, iters);
+    }
+    TSG_KERNEL_CHECK("k_peer_store");
+    return TSG_OK;
+}

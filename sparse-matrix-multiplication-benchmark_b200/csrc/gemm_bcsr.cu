@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_bcsr_gemm(const float *__restrict__ XT,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mt = blockIdx.y;
     const float *xt = XT + (size_t)mt * K * 128 + lane * 4;
-    const int mbase = mt * 128 + lane * 4;
+    const int mbase = mt * 128 + lane;  // XT tile layout: lane l's float4 holds rows l, l+32, l+64, l+96 (gemm_tcsc.cu)
     for (int col = blockIdx.x * 8 + warp; col < bc; col += gridDim.x * 8) {
         float acc[C][4];
 #pragma unroll
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_bcsr_gemm(const float *__restrict__ XT,
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const int m = mbase + v;
+            const int m = mbase + 32 * v;
             if (m >= M) continue;
 #pragma unroll
             for (int j = 0; j < C; ++j) {

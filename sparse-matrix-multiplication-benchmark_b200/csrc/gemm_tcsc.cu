@@ -34,6 +34,7 @@ constexpr int NTHREADS = (NWARP + 4) * 32;  // 4 compute warpgroups + 1 producer
 constexpr int REGS_COMPUTE = 112, REGS_PRODUCER = 24;
 constexpr int WOFF_BYTES = 160;  // (256/8 + 1) offsets, rounded up to 16 B
 constexpr int CNT_BYTES = 256;
+constexpr int TILE_PITCH = 260;  // words per row of the staged output tile (fused TMA epilogue)
 
 struct GemmParams {
     const float *XT;
@@ -50,12 +51,16 @@ struct GemmParams {
     float a;
     int use_prelu, order;
     uint32_t xstage_bytes, body_stage_bytes;
+    uint32_t bar_off;  // byte offset of the mbarriers: behind the stage ring (and behind the staged output tile if that is larger)
     // column-partitioned multi-GPU path: the epilogue additionally stores the finished slab into every peer's Y
     // (NVLink peer mappings, already offset to this rank's first column); 0 = single GPU
     int npeer;
     float *peerY[TSG_MAX_PEERS];
     // progress counters, one per 128-row tile: every compute warp bumps done[mt] once its part of a unit is stored, so
     // that stream-ordered peer copies (dist.cu, mode 2) can start on finished row blocks while the kernel still runs
+    // fused all-gather through the TMA engine (dist.cu mode 3): the finished tile is staged in shared memory and every
+    // 128-row x tn-column row segment goes to the local Y and to every peer with one bulk async store per row
+    int fused_tma;
     unsigned int *done;
     int ngroups;       // row tiles [gbound[g], gbound[g+1]) form progress group g (at most 8 groups)
     int gbound[9];
@@ -175,8 +180,9 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) {
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_bytes = p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.bar_off);
     uint64_t *empty = full + 2;
+    uint64_t *epi = full + 4;  // fused epilogue: consumers -> producer "the output tile has left shared memory"
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         mbar_init(&full[1], 1);
         mbar_init(&empty[0], NWARP);
         mbar_init(&empty[1], NWARP);
+        mbar_init(epi, NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -192,10 +199,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         // ===== producer warpgroup: hands its registers to the compute warpgroups; one thread feeds the two-stage ring =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
         if (warp == NWARP && lane == 0) {
-            uint32_t it = 0;
-            for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+            uint32_t it = 0, uidx = 0;
+            for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++uidx) {
                 const Unit un = decode_unit(p, u);
                 const int tn = un.cw * NWARP;
+                // fused epilogue: the previous unit's output tile overlays the stage ring until its bulk stores have read it
+                if (p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
                 const uint32_t woff_copy = (uint32_t)(((tn / 8 + 1) * 4 + 15) & ~15);
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int c = 0; c < p.nchunk; ++c, ++it) {
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         const Unit un = decode_unit(p, u);
         const int cw = un.cw;
         const int nbase = un.n0 + warp * cw;
-        const int mbase = un.mt * TM + lane * 4;
+        const int mbase = un.mt * TM + lane;  // lane l holds rows l, l+32, l+64, l+96 of the tile (XT position 4l+v)
         // the bias is re-read (L1/L2 hit) where it is needed instead of living in registers across the gather loops
         auto bias_of = [&](int j) { return (nbase + j < p.N) ? __ldg(p.B + nbase + j) : 0.f; };
 #pragma unroll
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                         const float t4[4] = {b + acc[j][0].x, b + acc[j][0].y, b + acc[j][1].x, b + acc[j][1].y};
 #pragma unroll
                         for (int v = 0; v < 4; ++v)
-                            if (mbase + v < p.M) p.Y[(size_t)(mbase + v) * p.ldy + nbase + j] = t4[v];
+                            if (mbase + 32 * v < p.M) p.Y[(size_t)(mbase + 32 * v) * p.ldy + nbase + j] = t4[v];
                     }
                     acc[j][0] = make_float2(0.f, 0.f);
                     acc[j][1] = acc[j][0];
@@ -270,11 +279,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             }
         }
         // ---- fused epilogue: bias, PReLU, store (and, on the multi-GPU path, the same store into every peer's Y) ----
+        if (p.fused_tma) asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp is done reading the stage ring
         const bool full_vec = vec_ok && (cw % 4 == 0) && (nbase + cw <= p.N);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const int m = mbase + v;
-            if (m >= p.M) continue;
+            const int m = mbase + 32 * v;
+            if (m >= p.M && !p.fused_tma) continue;
             float *yrow = p.Y + (size_t)m * p.ldy + nbase;
             float out[CWMAX];
 #pragma unroll
@@ -284,10 +294,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 float y = av;
                 if (j < cw) {
                     if (p.order == TSG_ORDER_BIAS_LAST) y = av + bias_of(j);                                   // tcsc.c:161
-                    else if (p.order == TSG_ORDER_SPLIT) y = ((nbase + j < p.N) ? yrow[j] : 0.f) - av;          // tcsc.c:138
+                    else if (p.order == TSG_ORDER_SPLIT) y = ((nbase + j < p.N && m < p.M) ? yrow[j] : 0.f) - av;          // tcsc.c:138
                     if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;                                              // tcsc.c:162
                 }
                 out[j] = y;
+            }
+            if (p.fused_tma) {
+                // stage this lane's cw values of row (lane + 32 v) into the output tile (row pitch 260 words: consecutive
+                // lanes = consecutive rows land 4 banks apart, so each quarter-warp float4 store covers all 32 banks)
+                float *trow = reinterpret_cast<float *>(smem) + (size_t)(lane + 32 * v) * TILE_PITCH + warp * cw;
+#pragma unroll
+                for (int j = 0; j < CWMAX; j += 4)
+                    if (j < cw) *reinterpret_cast<float4 *>(trow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                continue;
             }
             for (int q = -1; q < p.npeer; ++q) {  // q == -1: the local Y
                 float *row = (q < 0) ? yrow : p.peerY[q] + (size_t)m * p.ldy + nbase;
@@ -302,6 +321,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 }
             }
         }
+        if (p.fused_tma) {
+            // tile complete in shared memory -> one bulk async store (TMA engine) per row and destination
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (tid < TM) {
+                const int m = un.mt * TM + tid;
+                const int ncol = min(cw * NWARP, p.N - un.n0);
+                if (m < p.M && ncol > 0) {
+                    const uint32_t src = smem_addr(reinterpret_cast<float *>(smem) + (size_t)tid * TILE_PITCH);
+                    const uint32_t bytes = (uint32_t)ncol * 4u;
+                    for (int q = -1; q < p.npeer; ++q) {
+                        float *dst = ((q < 0) ? p.Y : p.peerY[q]) + (size_t)m * p.ldy + un.n0;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be overwritten again
+            }
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (lane == 0) mbar_arrive(epi);
+        }
         if (p.done) {  // publish: this warp's share of unit (mt, n0) is in memory
             __threadfence_system();
             __syncwarp();
@@ -312,6 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             }
         }
     }
+    if (p.fused_tma && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
 }
 
 // ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
@@ -329,7 +370,9 @@ __global__ void __launch_bounds__(256) k_transpose_x(const float *__restrict__ X
     for (int i = 0; i < 4; ++i) {
         const int k = k0 + ty + 8 * i, m = m0 + tx;
         if (k < K) {
-            const int mt = m / TM, ml = m % TM;
+            // position inside the tile: row r = l + 32 v sits at 4 l + v, so that lane l's float4 holds rows l, l+32, l+64, l+96
+            // (consecutive lanes = consecutive rows: conflict-free staging of the output tile, see the fused epilogue)
+            const int mt = m / TM, r = m % TM, ml = 4 * (r & 31) + (r >> 5);
             XT[((size_t)mt * K + k) * TM + ml] = tile[tx][ty + 8 * i];
         }
     }
@@ -535,7 +578,7 @@ using namespace tsg;
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma);
 }
 
 extern "C" {
@@ -570,22 +613,28 @@ int tsg_profile_read(double *total_ms, int *launches) {
 
 int tsg_tcsc_gemm(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                   long long ldy) {
-    return tcsc_gemm_peers(W, X, B, a, use_prelu, order, Y, M, N, K, ldy, 0, nullptr, nullptr, nullptr);
+    return tcsc_gemm_peers(W, X, B, a, use_prelu, order, Y, M, N, K, ldy, 0, nullptr, nullptr, nullptr, 0);
 }
 
 }  // extern "C"
 
 namespace tsg {
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog) {
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma) {
     TSG_TRY(ensure_device());
     if (npeer < 0 || npeer > TSG_MAX_PEERS) return set_error(TSG_EINVAL, "too many peers");
     if (!W || !X || !B || !Y) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: null argument");
     if (N != W->cols || K != W->rows) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: W is %d x %d but K=%d, N=%d", W->rows, W->cols, K, N);
     if (order < 0 || order > 2) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
     if (ldy < N) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: ldy < N");
+    if (!fused_tma && npeer == 0 && !done) {  // TSG_FUSED_EPILOGUE=1: route the single-GPU store through the TMA epilogue too
+        static const int env_fused = getenv("TSG_FUSED_EPILOGUE") ? atoi(getenv("TSG_FUSED_EPILOGUE")) : 0;
+        if (env_fused && M >= TSG_SKINNY_M && !(N & 3) && !(ldy & 3) && !(reinterpret_cast<uintptr_t>(Y) & 15)) fused_tma = 1;
+    }
+    if (fused_tma && ((N & 3) || (ldy & 3) || (reinterpret_cast<uintptr_t>(Y) & 15)))
+        return set_error(TSG_EUNSUPPORTED, "fused TMA epilogue needs N, ldy multiples of 4 and a 16-byte aligned Y");
     if (M <= 0 || N <= 0) return TSG_OK;
-    const bool skinny = npeer == 0 && !done && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
+    const bool skinny = npeer == 0 && !done && !fused_tma && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
     if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
 
     TSG_TRY(build_kstream(W));
@@ -602,7 +651,10 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     for (int q = 0; q < TSG_MAX_PEERS; ++q) p.peerY[q] = (q < npeer) ? peerY[q] : nullptr;
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
-    const size_t smem_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES) + 64;
+    size_t ring_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES);
+    if (fused_tma && ring_bytes < (size_t)TM * TILE_PITCH * 4) ring_bytes = (size_t)TM * TILE_PITCH * 4;  // tiny K: the tile is the larger one
+    p.bar_off = (uint32_t)ring_bytes;
+    const size_t smem_bytes = ring_bytes + 64;
     // unit decomposition: full 256-column tiles for as many complete rounds of the persistent grid as there are, the
     // left-over tiles cut into 2 or 4 narrower units each so that the last round is short (tail balancing)
     const int sms = num_sms();
@@ -620,6 +672,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         }
     }
     p.units_total = p.units_full + R * p.sub;
+    p.fused_tma = fused_tma;
     p.done = done;
     p.ngroups = 0;
     for (int g = 0; g < 9; ++g) p.gbound[g] = 0;

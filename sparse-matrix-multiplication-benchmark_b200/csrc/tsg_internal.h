@@ -114,7 +114,7 @@ struct Progress {
 };
 // tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
-                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog);
+                    long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma = 0);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
 int transpose_x_tiles(const float *X, float *XT, int M, int K);
 }  // namespace tsg

@@ -113,7 +113,7 @@ def _gpu_worker(rank, world, port_no, M, K, N, mode, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["nccl_allgather", "fused_peer_stores", "copy_engine_overlap"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["nccl_allgather", "fused_peer_stores", "copy_engine_overlap", "fused_tma_stores"])
 def test_two_gpus_bit_exact(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
