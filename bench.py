@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
-    ap.add_argument("--dist-mode", type=int, default=2, choices=[0, 1, 2, 3])
+    ap.add_argument("--dist-mode", type=int, default=3, choices=[0, 1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

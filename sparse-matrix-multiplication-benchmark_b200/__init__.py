@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtsgemm_b200.so")
+LIB_PATH = os.environ.get("TSG_LIB_PATH") or os.path.join(HERE, "libtsgemm_b200.so")  # TSG_LIB_PATH: A/B another build of the SAME library
 
 ORDER_BIAS_FIRST, ORDER_BIAS_LAST, ORDER_SPLIT = 0, 1, 2
 SKINNY_M = 32

@@ -357,30 +357,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
 
 // ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
 __global__ void __launch_bounds__(256) k_transpose_x(const float *__restrict__ X, float *__restrict__ XT, int M, int K) {
-    __shared__ float tile[32][33];
-    const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    // one CTA = one 128-row tile x 32 k: coalesced reads along k, then every thread writes a float4 holding rows
+    // l, l+32, l+64, l+96 of one k (position 4l..4l+3 of the tile row) -> a warp writes 512 contiguous bytes
+    __shared__ float tile[TM][33];
+    const int k0 = blockIdx.x * 32, mt = blockIdx.y, m0 = mt * TM;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty + 8 * i, k = k0 + tx;
-        tile[ty + 8 * i][tx] = (m < M && k < K) ? __ldg(X + (size_t)m * K + k) : 0.f;
+    for (int i = 0; i < TM / 8; ++i) {
+        const int r = ty + 8 * i, m = m0 + r, k = k0 + tx;
+        tile[r][tx] = (m < M && k < K) ? __ldg(X + (size_t)m * K + k) : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int k = k0 + ty + 8 * i, m = m0 + tx;
+        const int kk = ty + 8 * i, k = k0 + kk;
         if (k < K) {
-            // position inside the tile: row r = l + 32 v sits at 4 l + v, so that lane l's float4 holds rows l, l+32, l+64, l+96
-            // (consecutive lanes = consecutive rows: conflict-free staging of the output tile, see the fused epilogue)
-            const int mt = m / TM, r = m % TM, ml = 4 * (r & 31) + (r >> 5);
-            XT[((size_t)mt * K + k) * TM + ml] = tile[tx][ty + 8 * i];
+            const float4 v = make_float4(tile[tx][kk], tile[tx + 32][kk], tile[tx + 64][kk], tile[tx + 96][kk]);
+            *reinterpret_cast<float4 *>(XT + ((size_t)mt * K + k) * TM + 4 * tx) = v;
         }
     }
 }
 
 int transpose_x_tiles(const float *X, float *XT, int M, int K) {
     const int mtiles = (M + TM - 1) / TM;
-    dim3 grid((K + 31) / 32, mtiles * (TM / 32));
+    dim3 grid((K + 31) / 32, mtiles);
     k_transpose_x<<<grid, 256, 0, stream()>>>(X, XT, M, K);
     TSG_KERNEL_CHECK("k_transpose_x");
     return TSG_OK;
