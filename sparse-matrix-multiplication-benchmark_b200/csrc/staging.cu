@@ -1,4 +1,6 @@
 // staging.cu -- host<->device staging for the reference-named entry points (callers hand us host buffers).
+#include <cstdlib>
+
 #include "tsg_host_shim.h"
 #include "tsg_internal.h"
 
@@ -57,10 +59,12 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     }
     TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
     // slabs: multiples of 128 rows (the kernel's row tile).  PCIe is the bottleneck of a host-pointer call, so the slabs
-    // are kept small (about 512 rows, at most 16 of them): the un-overlapped head (first H2D) and tail (last kernel +
+    // are kept small (about 256 rows, at most 32 of them; TSG_HOST_SLAB_ROWS overrides): the un-overlapped head (first H2D) and tail (last kernel +
     // last D2H) shrink with the slab, and the kernel's lower efficiency on small slabs hides under the copies
-    int nslab = (M + 511) / 512;
-    if (nslab > 16) nslab = 16;
+    int slab_rows = 256;
+    if (const char *e = getenv("TSG_HOST_SLAB_ROWS")) slab_rows = atoi(e) > 0 ? atoi(e) : 256;
+    int nslab = (M + slab_rows - 1) / slab_rows;
+    if (nslab > 32) nslab = 32;
     if (nslab < 4) nslab = (M + 127) / 128 < 4 ? (M + 127) / 128 : 4;
     int slab = (((M + nslab - 1) / nslab) + 127) / 128 * 128;
     if (M < TSG_SKINNY_M) slab = M;
