@@ -19,3 +19,16 @@ def test_reference_test_bcsr_program_passes_on_the_product():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "Test passed! Results match." in out.stdout, out.stdout  # test/test_bcsr.cpp:37
+
+
+def test_reference_sparsegemm_driver_passes_on_the_product():
+    """Source-level drop-in: the reference's SparseGEMM.cpp, compiled unchanged against include/SparseGEMM.h, validates
+    sparseGEMM / sparseGEMM_PReLU against its own CPU dense GEMM (compare_results, abs 1e-5).  The full run takes over a
+    minute (it is a benchmark), so it is cut after 25 s: at least the first cases must have been reported, none failed."""
+    exe = os.path.join(ge.ROOT, "oracle", "_ref", "ref_sparsegemm_on_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built (needs /root/reference at build time)")
+    out = subprocess.run(["timeout", "25", "stdbuf", "-oL", exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode in (0, 124), out.stderr
+    assert "Test case not passed" not in out.stdout, out.stdout
+    assert out.stdout.count("sGEMM_PReLU cycles=") >= 3, out.stdout
