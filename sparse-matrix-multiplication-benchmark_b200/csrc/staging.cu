@@ -74,7 +74,7 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     if (saved_kernel == 0 && M >= TSG_SKINNY_M) tsg_tcsc_set_kernel(1);
     const int nbuf = nslab < 3 ? nslab : 3;
     float *dX[3] = {nullptr, nullptr, nullptr}, *dY[3] = {nullptr, nullptr, nullptr}, *dB = nullptr;
-    cudaEvent_t ev_in[3], ev_k[3], ev_out[3];
+    static thread_local cudaEvent_t ev_in[3] = {nullptr}, ev_k[3] = {nullptr}, ev_out[3] = {nullptr};  // created once per thread
     int rc = TSG_OK;
     tsg_set_stream(s_k);
     int b_owned = 0;
@@ -84,9 +84,11 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     for (int i = 0; i < nbuf && !rc; ++i) {
         rc = dev_alloc_t(&dX[i], (size_t)slab * K);
         if (!rc) rc = dev_alloc_t(&dY[i], (size_t)slab * N);
-        cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+        if (!ev_in[i]) {
+            cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+        }
     }
     if (!rc) rc = build_kstream(W);  // on s_k
     cudaStreamSynchronize(s_k);      // pool allocations above are ordered on s_k; the copy streams use them next
@@ -115,7 +117,6 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     for (int i = 0; i < nbuf; ++i) {
         dev_free(dX[i]);
         dev_free(dY[i]);
-        cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_k[i]); cudaEventDestroy(ev_out[i]);
     }
     tsg_shim_release(dB, b_owned);
     cudaStreamSynchronize(s_k);
