@@ -167,17 +167,27 @@ static int tcsc_from_dense_impl(const T *dense, int rows, int cols, tsg_tcsc **o
     unsigned long long *cc = nullptr;
     int *totals = nullptr;
     int rc = TSG_OK;
+    bool ws_held = false;
     auto fail = [&](int code) {
-        dev_free(pm); dev_free(nm); dev_free(cc); dev_free(totals);
+        if (ws_held) ws_release(2);
         tsg_tcsc_destroy(W);
         return code;
     };
     if ((rc = dev_alloc_t(&W->csp, (size_t)N + 1))) return fail(rc);
     if ((rc = dev_alloc_t(&W->csn, (size_t)N + 1))) return fail(rc);
-    if ((rc = dev_alloc_t(&pm, (size_t)S * N))) return fail(rc);
-    if ((rc = dev_alloc_t(&nm, (size_t)S * N))) return fail(rc);
-    if ((rc = dev_alloc_t(&cc, (size_t)N + 1))) return fail(rc);
-    if ((rc = dev_alloc_t(&totals, 2))) return fail(rc);
+    {   // scratch (ballot masks, packed column counts, totals) lives in a persistent per-thread workspace: converting
+        // matrix after matrix must not churn the memory pool (a pool growth costs tens of milliseconds)
+        const size_t mask_bytes = (((size_t)S * N * 4) + 255) & ~(size_t)255;
+        const size_t cc_bytes = ((((size_t)N + 1) * 8) + 255) & ~(size_t)255;
+        void *base = nullptr;
+        if ((rc = ws_acquire(2, 2 * mask_bytes + cc_bytes + 256, &base))) return fail(rc);
+        ws_held = true;
+        char *b = static_cast<char *>(base);
+        pm = reinterpret_cast<uint32_t *>(b);
+        nm = reinterpret_cast<uint32_t *>(b + mask_bytes);
+        cc = reinterpret_cast<unsigned long long *>(b + 2 * mask_bytes);
+        totals = reinterpret_cast<int *>(b + 2 * mask_bytes + cc_bytes);
+    }
     if (cudaMemsetAsync(cc, 0, ((size_t)N + 1) * sizeof(unsigned long long), st) != cudaSuccess) return fail(set_error(TSG_ECUDA, "memset failed"));
     if (N > 0 && S > 0) {
         dim3 grid((N + 127) / 128, S);
@@ -201,7 +211,7 @@ static int tcsc_from_dense_impl(const T *dense, int rows, int cols, tsg_tcsc **o
         if (cudaGetLastError() != cudaSuccess) return fail(set_error(TSG_ECUDA, "launch of k_tcsc_fill failed"));
         count_launch();
     }
-    dev_free(pm); dev_free(nm); dev_free(cc); dev_free(totals);
+    ws_release(2);
     *out = W;
     return TSG_OK;
 }
@@ -283,7 +293,7 @@ int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t 
     cudaStream_t st = stream();
     const int nb = (int)((n + 4095) / 4096);
     uint32_t *sums = nullptr;
-    TSG_TRY(dev_alloc_t(&sums, (size_t)nb + 1));
+    TSG_TRY(ws_acquire(4, ((size_t)nb + 1) * sizeof(uint32_t), reinterpret_cast<void **>(&sums)));
     if (nb > 0) {
         k_scan_l1<<<nb, 1024, 0, st>>>(in, out, n, sums);
         TSG_KERNEL_CHECK("k_scan_l1");
@@ -294,7 +304,7 @@ int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t 
         k_scan_l3<<<nb, 1024, 0, st>>>(out, n, sums);
         TSG_KERNEL_CHECK("k_scan_l3");
     }
-    return dev_free(sums);
+    return ws_release(4);
 }
 
 // =====================================================================================================================

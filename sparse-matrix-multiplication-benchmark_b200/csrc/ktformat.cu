@@ -131,17 +131,24 @@ int build_kstream(tsg_tcsc *W) {
         int rc;
         uint32_t *gwords = nullptr, *total = nullptr;
         int *maxw = nullptr;
+        bool ws_held = false;
         auto fail = [&](int code) {
-            dev_free(gwords); dev_free(total); dev_free(maxw);
+            if (ws_held) ws_release(3);
             free_kstream(ks);
             return code;
         };
         if ((rc = dev_alloc_t(&ks.cnt, (size_t)nplanes * ks.ncols_pad))) return fail(rc);
         if ((rc = dev_alloc_t(&ks.woff, (size_t)ngroups_total + 8))) return fail(rc);
         if ((rc = dev_alloc_t(&ks.body, (size_t)ks.body_words))) return fail(rc);
-        if ((rc = dev_alloc_t(&gwords, (size_t)ngroups_total + 8))) return fail(rc);
-        if ((rc = dev_alloc_t(&total, 1))) return fail(rc);
-        if ((rc = dev_alloc_t(&maxw, 1))) return fail(rc);
+        {   // scratch from the persistent workspace (no pool churn when matrices are converted again and again)
+            const size_t gw_bytes = ((((size_t)ngroups_total + 8) * 4) + 255) & ~(size_t)255;
+            void *base = nullptr;
+            if ((rc = ws_acquire(3, gw_bytes + 512, &base))) return fail(rc);
+            ws_held = true;
+            gwords = static_cast<uint32_t *>(base);
+            total = reinterpret_cast<uint32_t *>(static_cast<char *>(base) + gw_bytes);
+            maxw = reinterpret_cast<int *>(static_cast<char *>(base) + gw_bytes + 256);
+        }
         cudaMemsetAsync(maxw, 0, sizeof(int), st);
         cudaMemsetAsync(ks.body, 0xFF, (size_t)ks.body_words * 4, st);
         cudaMemsetAsync(gwords, 0, ((size_t)ngroups_total + 8) * 4, st);
@@ -175,8 +182,8 @@ int build_kstream(tsg_tcsc *W) {
             cudaMemcpyAsync(&h_total, total, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess)
             return fail(set_error(TSG_ECUDA, "build_kstream: device failure: %s", cudaGetErrorString(cudaGetLastError())));
-        dev_free(gwords); dev_free(total); dev_free(maxw);
-        gwords = nullptr; total = nullptr; maxw = nullptr;
+        ws_release(3);
+        ws_held = false;
         if ((long long)h_total > ks.body_words) {
             free_kstream(ks);
             return set_error(TSG_ECUDA, "build_kstream: internal size bound violated (%u > %lld)", h_total, ks.body_words);

@@ -74,7 +74,7 @@ int dev_alloc(void **out, size_t bytes) {
 }
 
 // ---- per-thread workspaces that survive across calls (XT / XS): no cudaMallocAsync + cudaFreeAsync per GEMM ------------
-static thread_local Workspace g_ws[2];
+static thread_local Workspace g_ws[5];
 
 int ws_acquire(int slot, size_t bytes, void **out) {
     Workspace &w = g_ws[slot];

@@ -47,7 +47,8 @@ int ensure_device();  // TSG_OK iff a usable sm_100 device is current (cached)
 
 int dev_alloc(void **out, size_t bytes);
 int dev_free(void *p);
-// workspace that persists across calls on this thread (slot 0: XT tiles, slot 1: skinny X pack); stream-safe: a
+// workspace that persists across calls on this thread (slot 0: XT tiles, 1: skinny X pack, 2: conversion scratch,
+// 3: gather-stream build scratch, 4: scan block sums); stream-safe: a
 // user on another stream is ordered behind the previous one with an event
 struct Workspace {
     void *p = nullptr;
