@@ -381,7 +381,7 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
 namespace tsg {
 
 __global__ void __launch_bounds__(512) k_peer_store_scattered(float *__restrict__ dst, long long ld, int rows, int cols, int iters) {
-    // CTA b owns row tile (b % mt), column tile (b / mt); 16 warps x 16 columns, lane l rows 4l..4l+3 (as k_tcsc_gemm)
+    // CTA b owns row tile (b % mt), column tile (b / mt); 16 warps x 16 columns, every lane four rows of 64 contiguous bytes (the pattern of mode 1's epilogue)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mtiles = rows / 128, ntiles = cols / 256;
     for (int it = 0; it < iters; ++it)

@@ -12,7 +12,7 @@
 // for ternary block values the product is exact either way).
 //
 // Mapping: a CTA owns 128 rows of X (the K-major tile XT[mtile][k][128] shared with the TCSC kernel); every warp
-// owns one block-column at a time (C output columns), lane l holds rows 4l..4l+3 -> C x 4 accumulators per thread.
+// owns one block-column at a time (C output columns), lane l holds rows l, l+32, l+64, l+96 (one float4 of XT per k) -> C x 4 accumulators per thread.
 // X rows are read straight from the L2-resident XT tile with coalesced 512-byte warp loads.
 #include "tsg_internal.h"
 

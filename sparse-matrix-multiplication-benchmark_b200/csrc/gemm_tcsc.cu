@@ -4,7 +4,7 @@
 // (sparse/tcsc.c:69-165,179-275) and sparseGEMM<float> / sparseGEMM_PReLU<float> (SparseGEMM.h:104-119,151-168).
 //
 // Tiled kernel (M >= TSG_SKINNY_M).  One persistent CTA per SM walks work units (128 rows of X) x (TN columns of W):
-//   * lanes own rows: lane l of every warp holds rows 4l..4l+3 of the 128-row tile, a warp owns CW columns, so each
+//   * lanes own rows: lane l of every warp holds rows l, l+32, l+64, l+96 of the 128-row tile, a warp owns CW columns, so each
 //     thread keeps CW x 4 accumulators in registers and the k index of every non-zero is warp-uniform;
 //   * X is pre-transposed once per call into K-major 128-row tiles XT[mtile][k][128] (transpose_x_tiles), so that a
 //     kc-row chunk of a tile is ONE contiguous block: a producer thread streams chunk after chunk into a two-stage
@@ -96,7 +96,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 // ---- gather-add over one chunk for the columns of a warp ---------------------------------------------------------------
-// Accumulators are kept as packed fp32x2 pairs (rows 4l,4l+1 and 4l+2,4l+3 of the tile) so that one FADD2 (add.f32x2,
+// Accumulators are kept as packed fp32x2 pairs (rows l,l+32 and l+64,l+96 of the tile) so that one FADD2 (add.f32x2,
 // sm_100) retires two adds per issue slot; each component is an ordinary IEEE fp32 add, so the roundings are unchanged.
 // One 32-bit word of the gather stream holds up to four non-zeros; a 0xFF byte is padding: its load and adds are
 // predicated off, so it costs issue slots but no shared-memory bandwidth.  Adds are applied in stream order.
