@@ -98,16 +98,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // ---- gather-add over one chunk for the columns of a warp ---------------------------------------------------------------
 // Accumulators are kept as packed fp32x2 pairs (rows l,l+32 and l+64,l+96 of the tile) so that one FADD2 (add.f32x2,
 // sm_100) retires two adds per issue slot; each component is an ordinary IEEE fp32 add, so the roundings are unchanged.
-// One 32-bit word of the gather stream holds up to four non-zeros; a 0xFF byte is padding: its load and adds are
-// predicated off, so it costs issue slots but no shared-memory bandwidth.  Adds are applied in stream order.
+// One 32-bit word of the gather stream holds up to four non-zeros (bytes k+1); a 0 byte is padding: its load and adds
+// are predicated off, so it costs issue slots but no shared-memory bandwidth.  Adds are applied in stream order.
 template <bool NEG>
 __device__ __forceinline__ void gather_word(float2 &a01, float2 &a23, uint32_t word, uint32_t xbase) {
+    // Entry bytes hold k+1 (1..kc), 0 is padding.  Masking the byte in place gives the value and the "not padding"
+    // predicate in one LOP3; the row's byte offset (k+1)*512 is then one IMAD / IMAD.HI on the still-shifted field
+    // (xbase already has the -512 folded in), so an entry costs 5 instructions: LOP3, IMAD, LDS.128, 2 x FADD2.
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const uint32_t k = __byte_perm(word, 0u, 0x4440u + e);  // byte e, zero-extended (one PRMT)
-        if (k != 0xFFu) {  // warp-uniform: compiles to predicated LDS.128 + FADD2, no branch
+        const uint32_t f = word & (0xFFu << (8 * e));
+        if (f != 0u) {  // warp-uniform: compiles to predicated LDS.128 + FADD2, no branch
+            uint32_t addr;
+            if (e == 0) addr = f * (TM * 4) + xbase;
+            else if (e == 1) addr = f * (TM * 4 / 256) + xbase;
+            else if (e == 2) addr = __umulhi(f, 1u << 25) + xbase;   // (f >> 16) * 512 = f >> 7
+            else addr = __umulhi(f, 1u << 17) + xbase;               // (f >> 24) * 512 = f >> 15
             float4 x;  // 32-bit shared-window address: no generic->shared conversion per load
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(k * (TM * 4) + xbase));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
             if (NEG) {
                 a01 = __fadd2_rn(a01, make_float2(-x.x, -x.y));
                 a23 = __fadd2_rn(a23, make_float2(-x.z, -x.w));
@@ -146,11 +154,11 @@ __device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t x
             const uint4 w = nxt;  // one uniform-address LDS.128 = up to 16 non-zeros
             nxt = *++qp;
             gather_word<NEG>(acc[j][0], acc[j][1], w.x, xbase);
-            if (w.y != 0xFFFFFFFFu) {  // entries are packed from the front: an all-padding word ends the list
+            if (w.y != 0u) {  // entries are packed from the front: an all-padding word ends the list
                 gather_word<NEG>(acc[j][0], acc[j][1], w.y, xbase);
-                if (w.z != 0xFFFFFFFFu) {
+                if (w.z != 0u) {
                     gather_word<NEG>(acc[j][0], acc[j][1], w.z, xbase);
-                    if (w.w != 0xFFFFFFFFu) gather_word<NEG>(acc[j][0], acc[j][1], w.w, xbase);
+                    if (w.w != 0u) gather_word<NEG>(acc[j][0], acc[j][1], w.w, xbase);
                 }
             }
         }
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const uint32_t s = it & 1u;
                 mbar_wait(&full[s], (it >> 1) & 1u);
                 const uint8_t *st = smem + (size_t)s * stage_bytes;
-                const uint32_t xbase = smem_addr(st) + lane * 16;
+                const uint32_t xbase = smem_addr(st) + lane * 16 - TM * 4;  // entries are k+1: fold the -512 in here
                 const uint32_t *body_s = reinterpret_cast<const uint32_t *>(st + p.xstage_bytes);
                 const uint8_t *cnt_s = st + p.xstage_bytes + p.body_stage_bytes;
                 const uint32_t *woff_s = reinterpret_cast<const uint32_t *>(cnt_s + CNT_BYTES);

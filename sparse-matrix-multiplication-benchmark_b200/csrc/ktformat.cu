@@ -11,7 +11,7 @@
 // Layout (see tsg::KStream): plane p = sign*nchunk + chunk.
 //   cnt [p][ncols_pad]      uint8   16-byte quads (4 words = 16 entries) used by the column's list in this plane
 //   woff[p*ngroup + g]      uint32  word offset into `body` of 8-column group g (always a multiple of 4 words = 16 B)
-//   body[...]               uint32  entries: one byte per non-zero = k - chunk*kc, every list padded with 0xFF to a whole
+//   body[...]               uint32  entries: one byte per non-zero = k - chunk*kc + 1, every list padded with 0 to a whole
 //                                   quad, so that the kernel fetches a list with ONE uniform 16-byte shared-memory load
 //                                   per 16 entries (the index fetch competes with the gathers for the same crossbar)
 // Size: ~1.6 bytes per non-zero at 90 % sparsity (vs 4 bytes in the int32 TCSC arrays).
@@ -82,12 +82,12 @@ __global__ void k_ks_fill(const int *__restrict__ csp, const int *__restrict__ c
     uint32_t off = woff[(size_t)plane * ngroup + (n >> 3)];
     for (int i = 0; i < (n & 7); ++i) off += 4u * cp[i];
     const int k0 = c * kc;
-    const int padded = ((hi - lo + 15) >> 4) << 4;  // whole quads; the tail is 0xFF
+    const int padded = ((hi - lo + 15) >> 4) << 4;  // whole quads; the tail is 0 (padding)
     for (int t = 0; t < padded; t += 4) {
         uint32_t w = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint32_t kk = (lo + t + q < hi) ? (uint32_t)(ri[lo + t + q] - k0) : 0xFFu;
+            uint32_t kk = (lo + t + q < hi) ? (uint32_t)(ri[lo + t + q] - k0 + 1) : 0u;  // k+1; 0 = padding
             w |= kk << (8 * q);
         }
         body[off++] = w;
@@ -150,7 +150,7 @@ int build_kstream(tsg_tcsc *W) {
             maxw = reinterpret_cast<int *>(static_cast<char *>(base) + gw_bytes + 256);
         }
         cudaMemsetAsync(maxw, 0, sizeof(int), st);
-        cudaMemsetAsync(ks.body, 0xFF, (size_t)ks.body_words * 4, st);
+        cudaMemsetAsync(ks.body, 0, (size_t)ks.body_words * 4, st);
         cudaMemsetAsync(gwords, 0, ((size_t)ngroups_total + 8) * 4, st);
         {
             dim3 grid((ks.ncols_pad + 255) / 256, nplanes);
