@@ -84,6 +84,13 @@ int tsg_tcsc_gemm(tsg_tcsc *W, const float *X_dev, const float *B_dev, float a, 
 /* force one kernel: 0 auto, 1 tiled shared-memory gather kernel, 2 skinny kernel */
 int tsg_tcsc_set_kernel(int which);
 int tsg_tcsc_get_kernel(void);
+/* planning hooks of the tiled kernel -- pure host arithmetic, no device needed (tests/test_plan.py).
+ * tsg_plan_units: out5 = {row tiles, 256-column tiles, full units, sub, total units}; tsg_plan_unit_at: out3 = {row tile,
+ * first column, columns per warp} of unit u; tsg_plan_progress: the progress groups of the multi-GPU mode 2 and the
+ * number of arrivals each group's counter will see. */
+int tsg_plan_units(int M, int N, int sms, int out5[5]);
+int tsg_plan_unit_at(int M, int N, int sms, int u, int out3[3]);
+int tsg_plan_progress(int M, int N, int sms, int *ngroups, int gbound9[9], unsigned int target8[8]);
 /* per-launch CUDA-event timing of the tiled GEMM kernel on its launching stream (bench.py's roofline numerator) */
 int tsg_profile_enable(int on);
 int tsg_profile_read(double *total_ms, int *launches);

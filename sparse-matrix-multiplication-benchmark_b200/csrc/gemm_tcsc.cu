@@ -170,20 +170,21 @@ __device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t x
 struct Unit {
     int mt, n0, cw;
 };
-__device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) {
+__host__ __device__ __forceinline__ Unit decode_unit_raw(int units_full, int sub, int ntiles, int u) {
     int fu = u, part = 0, cw = CWMAX;
-    if (u >= p.units_full) {
-        const int v = u - p.units_full;
-        fu = p.units_full + v / p.sub;
-        part = v % p.sub;
-        cw = CWMAX / p.sub;
+    if (u >= units_full) {
+        const int v = u - units_full;
+        fu = units_full + v / sub;
+        part = v % sub;
+        cw = CWMAX / sub;
     }
     Unit r;
-    r.mt = fu / p.ntiles;
+    r.mt = fu / ntiles;
     r.cw = cw;
-    r.n0 = (fu % p.ntiles) * (CWMAX * NWARP) + part * (cw * NWARP);
+    r.n0 = (fu % ntiles) * (CWMAX * NWARP) + part * (cw * NWARP);
     return r;
 }
+__device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) { return decode_unit_raw(p.units_full, p.sub, p.ntiles, u); }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -558,6 +559,57 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
     return ws_release(1);
 }
 
+// ---- host-side planning (pure arithmetic; also exported for the CPU tests: tsg_plan_*) ---------------------------------
+struct UnitPlan {
+    int mtiles, ntiles, units_full, sub, units_total;
+};
+
+// unit decomposition: full 256-column tiles for as many complete rounds of the persistent grid as there are, the
+// left-over tiles cut into 2 or 4 narrower units each so that the last round is short (tail balancing)
+static UnitPlan plan_units(int M, int N, int sms) {
+    UnitPlan u;
+    u.mtiles = (M + TM - 1) / TM;
+    u.ntiles = (N + CWMAX * NWARP - 1) / (CWMAX * NWARP);
+    const int U = u.mtiles * u.ntiles;
+    u.units_full = (U / sms) * sms;
+    const int R = U - u.units_full;
+    u.sub = 1;
+    if (R > 0) {
+        // cost of the tail in full-unit times for sub = 1, 2, 4 (narrower units re-stream X, so prefer the smaller sub on ties)
+        double best = (double)((R + sms - 1) / sms);
+        for (int sub = 2; sub <= 4; sub *= 2) {
+            const double cost = (double)((R * sub + sms - 1) / sms) / sub * (1.0 + 0.04 * sub);
+            if (cost < best - 1e-9) { best = cost; u.sub = sub; }
+        }
+    }
+    u.units_total = u.units_full + R * u.sub;
+    return u;
+}
+
+// progress groups (dist.cu mode 2): three quarters of the row tiles in three big groups (they complete round by round of
+// the persistent grid anyway), then ever smaller ones so that little is left to push once the kernel retires; target[g] =
+// arrivals group g will see = one per compute warp per unit covering its row tiles
+static void plan_progress(const UnitPlan &u, Progress *prog) {
+    const double frac[8] = {0.25, 0.25, 0.25, 0.125, 0.0625, 0.03125, 0.015625, 1.0};
+    int b = 0, g = 0;
+    for (int i = 0; i < 9; ++i) prog->gbound[i] = 0;
+    while (b < u.mtiles && g < 8) {
+        int sz = (g == 7) ? u.mtiles - b : (int)(u.mtiles * frac[g] + 0.5);
+        if (sz < 1) sz = 1;
+        if (b + sz > u.mtiles) sz = u.mtiles - b;
+        b += sz;
+        prog->gbound[++g] = b;
+    }
+    prog->ngroups = g;
+    for (int i = 0; i < 8; ++i) prog->target[i] = 0;
+    for (int i = 0; i < g; ++i) {
+        unsigned int n = 0;
+        for (int mt = prog->gbound[i]; mt < prog->gbound[i + 1]; ++mt)
+            for (int nt = 0; nt < u.ntiles; ++nt) n += (mt * u.ntiles + nt < u.units_full) ? 1u : (unsigned int)u.sub;
+        prog->target[i] = n * NWARP;
+    }
+}
+
 static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
@@ -596,6 +648,31 @@ int tsg_tcsc_set_kernel(int which) {
     return TSG_OK;
 }
 int tsg_tcsc_get_kernel(void) { return g_force_kernel; }
+
+// planning hooks (pure host arithmetic, usable without a device): the unit decomposition and the progress groups
+int tsg_plan_units(int M, int N, int sms, int out5[5]) {
+    if (M <= 0 || N <= 0 || sms <= 0) return set_error(TSG_EINVAL, "tsg_plan_units: bad arguments");
+    const UnitPlan u = plan_units(M, N, sms);
+    out5[0] = u.mtiles; out5[1] = u.ntiles; out5[2] = u.units_full; out5[3] = u.sub; out5[4] = u.units_total;
+    return TSG_OK;
+}
+int tsg_plan_unit_at(int M, int N, int sms, int u, int out3[3]) {
+    if (M <= 0 || N <= 0 || sms <= 0) return set_error(TSG_EINVAL, "tsg_plan_unit_at: bad arguments");
+    const UnitPlan up = plan_units(M, N, sms);
+    if (u < 0 || u >= up.units_total) return set_error(TSG_EINVAL, "tsg_plan_unit_at: unit out of range");
+    const Unit un = decode_unit_raw(up.units_full, up.sub, up.ntiles, u);
+    out3[0] = un.mt; out3[1] = un.n0; out3[2] = un.cw;
+    return TSG_OK;
+}
+int tsg_plan_progress(int M, int N, int sms, int *ngroups, int gbound9[9], unsigned int target8[8]) {
+    if (M <= 0 || N <= 0 || sms <= 0) return set_error(TSG_EINVAL, "tsg_plan_progress: bad arguments");
+    Progress pr;
+    plan_progress(plan_units(M, N, sms), &pr);
+    *ngroups = pr.ngroups;
+    for (int i = 0; i < 9; ++i) gbound9[i] = pr.gbound[i];
+    for (int i = 0; i < 8; ++i) target8[i] = pr.target[i];
+    return TSG_OK;
+}
 
 // per-launch device timing of the tiled GEMM kernel (CUDA events on the launching stream)
 int tsg_profile_enable(int on) {
@@ -663,50 +740,19 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     if (fused_tma && ring_bytes < (size_t)TM * TILE_PITCH * 4) ring_bytes = (size_t)TM * TILE_PITCH * 4;  // tiny K: the tile is the larger one
     p.bar_off = (uint32_t)ring_bytes;
     const size_t smem_bytes = ring_bytes + 64;
-    // unit decomposition: full 256-column tiles for as many complete rounds of the persistent grid as there are, the
-    // left-over tiles cut into 2 or 4 narrower units each so that the last round is short (tail balancing)
-    const int sms = num_sms();
-    p.ntiles = (N + 255) / 256;
-    const int U = p.mtiles * p.ntiles;
-    p.units_full = (U / sms) * sms;
-    const int R = U - p.units_full;
-    p.sub = 1;
-    if (R > 0) {
-        // cost of the tail in full-unit times for sub = 1, 2, 4 (narrower units re-stream X, so prefer the smaller sub on ties)
-        double best = (double)((R + sms - 1) / sms);
-        for (int sub = 2; sub <= 4; sub *= 2) {
-            const double cost = (double)((R * sub + sms - 1) / sms) / sub * (1.0 + 0.04 * sub);
-            if (cost < best - 1e-9) { best = cost; p.sub = sub; }
-        }
-    }
-    p.units_total = p.units_full + R * p.sub;
+    const UnitPlan up = plan_units(M, N, num_sms());
+    p.ntiles = up.ntiles;
+    p.units_full = up.units_full;
+    p.sub = up.sub;
+    p.units_total = up.units_total;
     p.fused_tma = fused_tma;
     p.done = done;
     p.ngroups = 0;
     for (int g = 0; g < 9; ++g) p.gbound[g] = 0;
     if (done && prog) {
-        // progress groups: three quarters of the row tiles in three big groups (they complete round by round of the
-        // persistent grid anyway), then ever smaller ones so that little is left to push once the kernel retires
-        const double frac[8] = {0.25, 0.25, 0.25, 0.125, 0.0625, 0.03125, 0.015625, 1.0};
-        int b = 0, g = 0;
-        p.gbound[0] = 0;
-        while (b < p.mtiles && g < 8) {
-            int sz = (g == 7) ? p.mtiles - b : (int)(p.mtiles * frac[g] + 0.5);
-            if (sz < 1) sz = 1;
-            if (b + sz > p.mtiles) sz = p.mtiles - b;
-            b += sz;
-            p.gbound[++g] = b;
-        }
-        if (b < p.mtiles) p.gbound[g] = p.mtiles;
-        p.ngroups = g;
-        prog->ngroups = g;
-        for (int i = 0; i <= g; ++i) prog->gbound[i] = p.gbound[i];
-        for (int i = 0; i < g; ++i) {  // arrivals group i will see: one per compute warp per unit covering its row tiles
-            unsigned int n = 0;
-            for (int mt = p.gbound[i]; mt < p.gbound[i + 1]; ++mt)
-                for (int nt = 0; nt < p.ntiles; ++nt) n += (mt * p.ntiles + nt < p.units_full) ? 1u : (unsigned int)p.sub;
-            prog->target[i] = n * NWARP;
-        }
+        plan_progress(up, prog);
+        p.ngroups = prog->ngroups;
+        for (int i = 0; i <= prog->ngroups; ++i) p.gbound[i] = prog->gbound[i];
     }
     int rc = launch_tiled(p, smem_bytes);
     int rc2 = ws_release(0);

@@ -1,0 +1,82 @@
+"""Host-side planning of the tiled kernel, checked on the CPU (pure arithmetic in libtsgemm_b200.so, no device needed):
+the unit decomposition with tail balancing must cover every (row tile, column) exactly once, and the progress groups of
+the multi-GPU mode 2 must account for every arrival the kernel will make."""
+import ctypes as C
+
+import pytest
+
+import __graft_entry__ as ge
+
+SHAPES = [(4096, 4096), (64, 512), (8192, 14336), (16384, 16384), (129, 257), (33, 29), (1000, 100), (4096, 4096 * 8), (256, 4096), (32, 40)]
+
+
+@pytest.fixture(scope="module")
+def L():
+    t = ge.load()
+    lib = t.lib()
+    lib.tsg_plan_units.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 5)]
+    lib.tsg_plan_unit_at.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 3)]
+    lib.tsg_plan_progress.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int * 9), C.POINTER(C.c_uint * 8)]
+    return lib
+
+
+def plan(L, M, N, sms):
+    out = (C.c_int * 5)()
+    assert L.tsg_plan_units(M, N, sms, C.byref(out)) == 0
+    return list(out)
+
+
+@pytest.mark.parametrize("sms", [148, 132, 1, 7])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"M{m}N{n}" for m, n in SHAPES])
+def test_units_cover_every_tile_exactly_once(L, shape, sms):
+    M, N = shape
+    mtiles, ntiles, units_full, sub, total = plan(L, M, N, sms)
+    assert mtiles == -(-M // 128) and ntiles == -(-N // 256)
+    assert units_full % sms == 0 and units_full <= mtiles * ntiles and sub in (1, 2, 4)
+    assert total == units_full + (mtiles * ntiles - units_full) * sub
+    covered = {}
+    o = (C.c_int * 3)()
+    for u in range(total):
+        assert L.tsg_plan_unit_at(M, N, sms, u, C.byref(o)) == 0
+        mt, n0, cw = list(o)
+        assert 0 <= mt < mtiles and cw in (16, 8, 4) and n0 % 32 == 0 and n0 % (16 * cw) == 0
+        assert (cw == 16) == (u < units_full or sub == 1)
+        for c in range(n0, n0 + 16 * cw, 32):  # 32-column granules
+            assert (mt, c) not in covered, f"unit {u} overlaps unit {covered.get((mt, c))}"
+            covered[(mt, c)] = u
+    assert len(covered) == mtiles * ntiles * 8  # every 32-column granule of every 256-column tile of every row tile
+    # the tail is never longer than one round of full units would have been
+    tail_units = total - units_full
+    assert -(-tail_units // sms) / sub <= -(-(mtiles * ntiles - units_full) // sms) + 1e-9
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"M{m}N{n}" for m, n in SHAPES])
+def test_progress_groups_account_for_every_arrival(L, shape):
+    M, N = shape
+    sms = 148
+    mtiles, ntiles, units_full, sub, total = plan(L, M, N, sms)
+    ng, gb, tg = C.c_int(), (C.c_int * 9)(), (C.c_uint * 8)()
+    assert L.tsg_plan_progress(M, N, sms, C.byref(ng), C.byref(gb), C.byref(tg)) == 0
+    g = ng.value
+    bounds = list(gb)[: g + 1]
+    assert 1 <= g <= 8 and bounds[0] == 0 and bounds[-1] == mtiles and all(b1 > b0 for b0, b1 in zip(bounds, bounds[1:]))
+    assert sum(list(tg)[:g]) == total * 16  # one arrival per compute warp per unit
+    # recount independently from the unit list
+    per_group = [0] * g
+    o = (C.c_int * 3)()
+    for u in range(total):
+        L.tsg_plan_unit_at(M, N, sms, u, C.byref(o))
+        grp = max(i for i in range(g) if o[0] >= bounds[i])
+        per_group[grp] += 16
+    assert per_group == list(tg)[:g]
+    # group sizes shrink towards the end once there are enough row tiles
+    if mtiles >= 32:
+        sizes = [b1 - b0 for b0, b1 in zip(bounds, bounds[1:])]
+        assert sizes[0] >= sizes[-1] and sizes[-1] <= max(1, mtiles // 16)
+
+
+def test_plan_rejects_bad_arguments(L):
+    out = (C.c_int * 5)()
+    assert L.tsg_plan_units(0, 10, 148, C.byref(out)) != 0
+    o = (C.c_int * 3)()
+    assert L.tsg_plan_unit_at(128, 256, 148, 5, C.byref(o)) != 0
