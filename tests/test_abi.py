@@ -116,3 +116,22 @@ def test_partition_is_a_partition(t):
                     assert nc % 32 == 0
                 nxt = c0 + nc
             assert nxt == N
+
+
+def test_reference_programs_link_against_the_library():
+    """oracle/Makefile `drivers`: the reference's unmodified main.cpp / test_bcsr.cpp objects (compiled against the
+    reference's own headers) and its SparseGEMM.cpp (compiled against include/SparseGEMM.h) link against the library.
+    Built only where /root/reference exists; running them needs a B200 (tests/test_gpu_dropin.py)."""
+    if not os.path.isdir("/root/reference/sparse"):
+        pytest.skip("reference tree not present")
+    ge.build()
+    for exe in ("ref_main_on_b200", "ref_test_bcsr_on_b200", "ref_sparsegemm_on_b200"):
+        path = os.path.join(ROOT, "oracle", "_ref", exe)
+        assert os.path.exists(path), exe
+        needed = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+        assert "libtsgemm_b200.so" in needed, exe
+        undefined = subprocess.run(["nm", "-u", path], capture_output=True, text=True).stdout
+        if exe == "ref_main_on_b200":
+            assert "_Z22tcsc_sgemm_prelu_basicPfPK6tcsc_tS_fS_iii" in undefined  # resolved by the library at load time
+        if exe == "ref_sparsegemm_on_b200":
+            assert "tsg_sparse_gemm_f32" in undefined
