@@ -42,11 +42,23 @@ class bcsr_t(C.Structure):  # include/sparse/bcsr.h  (reference sparse/bcsr.h:7-
                 ("b_row_start", C.POINTER(C.c_int)), ("b_col_idx", C.POINTER(C.c_int)), ("b_values", C.POINTER(C.c_float))]
 
 
+def _build_in_tree() -> None:
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return
+    out = subprocess.run(["make", "-C", HERE, "-j8", "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise TsgError("building libtsgemm_b200.so failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+
+
 def lib() -> C.CDLL:
     """Load libtsgemm_b200.so (built in-tree by `make -C sparse-matrix-multiplication-benchmark_b200`)."""
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and "TSG_LIB_PATH" not in os.environ:
+        _build_in_tree()  # a source-only checkout: compile the CUDA library (nvcc, sm_100a), never substitute for it
     if not os.path.exists(LIB_PATH):
         raise TsgError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() -- there is no CPU fallback")
     L = C.CDLL(LIB_PATH)  # RTLD_LOCAL: our reference-named symbols must not interpose on other libraries
