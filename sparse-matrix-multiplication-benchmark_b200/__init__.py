@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.tsg_bcsr_dims.argtypes = [vp, ip, ip, ip, ip, ip]
     L.tsg_bcsr_download.argtypes = [vp, vp, vp, vp]
     L.tsg_bcsr_gemm.argtypes = [vp, vp, vp, f, i, vp, i, i, i, ll]
+    L.tsg_bcsr_set_kernel.argtypes = [i]
     L.tsg_gen_ternary_f32.argtypes = [vp, ll, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_ternary_i32.argtypes = [vp, ll, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_ternary_slice_f32.argtypes = [vp, i, i, i, i, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -384,6 +385,11 @@ def bcsr_sgemm_prelu_basic(X, W, B, a, N, Y=None):
 
 def bcsr_sgemm_prelu_avx(X, W, B, a, N, Y=None):
     return _bgemm("bcsr_sgemm_prelu_avx", X, W, B, a, Y, N)
+
+
+def bcsr_set_kernel(which: int) -> None:
+    """0 = default, 1 = plain kernel, 2 = shared-memory ring kernel (include/tsgemm_b200.h); both give the same bits."""
+    _check(lib().tsg_bcsr_set_kernel(int(which)), "tsg_bcsr_set_kernel")
 
 
 # =====================================================================================================================

@@ -166,6 +166,7 @@ void tsg_bcsr_destroy(tsg_bcsr *W) {
     if (!W) return;
     dev_free(W->row_start); dev_free(W->col_idx); dev_free(W->values);
     dev_free(W->cptr); dev_free(W->crow); dev_free(W->cblk);
+    dev_free(W->bs.cnt); dev_free(W->bs.wstart); dev_free(W->bs.eoff); dev_free(W->bs.hdr); dev_free(W->bs.val);
     delete W;
 }
 

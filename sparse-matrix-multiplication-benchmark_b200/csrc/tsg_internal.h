@@ -80,6 +80,25 @@ struct KStream {
     bool built = false;
 };
 
+// ---- private chunk-major stream of a BCSR matrix (gemm_bcsr_ring.cu) -------------------------------------------------
+// Run (tile, chunk) = the blocks of one 256-output-column tile whose block-row falls into chunk `chunk` (kcb block-rows),
+// ordered by (block-column, block-row) and padded to a multiple of 16 entries, so that a run's local block-rows (`hdr`,
+// one byte each) and its block values (`val`, r*c floats each) are each ONE contiguous, 16-byte aligned span.
+struct BStream {
+    int kcb = 0;      // block-rows per chunk (kcb * r <= 224 rows of X, kcb <= 255)
+    int nchunk = 0;   // ceil(br / kcb)
+    int ntile = 0;    // ceil(bc / tbc)
+    int tbc = 0;      // block-columns per tile = 256 / c
+    uint8_t *cnt = nullptr;      // [ntile*nchunk][256]  entries per block-column of the tile
+    uint32_t *wstart = nullptr;  // [ntile*nchunk][16]   first entry (relative to the run) of each compute warp
+    uint32_t *eoff = nullptr;    // [ntile*nchunk + 1]   first entry of each run
+    uint8_t *hdr = nullptr;      // [entries]            block-row inside the chunk
+    float *val = nullptr;        // [entries][r*c]
+    long long entries = 0;
+    int max_run = 0;             // longest run (entries, padded)
+    bool built = false, unsupported = false;
+};
+
 }  // namespace tsg
 
 // opaque handle of tsgemm_b200.h
@@ -98,6 +117,7 @@ struct tsg_bcsr {
     int *crow = nullptr;   // [k] block-row of each block in column-major order
     int *cblk = nullptr;   // [k] index of the block in `values`
     bool col_built = false;
+    tsg::BStream bs;
 };
 
 namespace tsg {
@@ -107,6 +127,10 @@ int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t 
 int is_device_pointer(const void *p);
 int build_kstream(tsg_tcsc *W);
 int bcsr_build_cols(tsg_bcsr *W);
+// ring kernel for BCSR (gemm_bcsr_ring.cu): *handled = 0 when the matrix does not fit its limits (caller falls back
+// to the plain kernel); XT = K-major 128-row tiles of X
+int bcsr_gemm_ring(tsg_bcsr *W, const float *XT, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy,
+                   int *handled);
 // progress groups of the tiled kernel (dist.cu mode 2): row tiles [gbound[g], gbound[g+1]) are complete when done[g] == target[g]
 struct Progress {
     int ngroups = 0;
