@@ -105,9 +105,9 @@ int tsg_bcsr_dims(const tsg_bcsr *W, int *r, int *c, int *br, int *bc, int *k);
 int tsg_bcsr_download(const tsg_bcsr *W, int *b_row_start, int *b_col_idx, float *b_values);
 int tsg_bcsr_gemm(tsg_bcsr *W, const float *X_dev, const float *B_dev, float a, int use_prelu, float *Y_dev,
                   int M, int N, int K, long long ldy);
-/* kernel selection for A/B runs: 0 = default (plain kernel; the shared-memory ring kernel when TSG_BCSR_RING=1 is set),
- * 1 = plain kernel, 2 = ring kernel (falls back to the plain one outside its limits: c not in {1,2,4,8,16}, r > 224).
- * Both produce the same bits. */
+/* kernel selection for A/B runs: 0 = default (the shared-memory ring kernel; the plain kernel when TSG_BCSR_RING=0 is
+ * set), 1 = plain kernel, 2 = ring kernel (falls back to the plain one outside its limits: c not in {1,2,4,8,16},
+ * r > 224).  Both produce the same bits. */
 int tsg_bcsr_set_kernel(int which);
 
 /* ---- device generators / verification (counter-based: element i is a pure function of (seed, i)) --------------- */

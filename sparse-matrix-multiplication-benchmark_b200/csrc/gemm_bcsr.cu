@@ -141,7 +141,7 @@ __global__ void k_bcsr_tail_bias(const float *__restrict__ B, float a, int use_p
 
 using namespace tsg;
 
-static thread_local int g_bcsr_kernel = 0;  // 0 = default (plain kernel unless TSG_BCSR_RING=1), 1 = plain, 2 = ring
+static thread_local int g_bcsr_kernel = 0;  // 0 = default (ring kernel unless TSG_BCSR_RING=0), 1 = plain, 2 = ring
 
 extern "C" int tsg_bcsr_set_kernel(int which) {
     if (which < 0 || which > 2) return set_error(TSG_EINVAL, "tsg_bcsr_set_kernel: 0 (default), 1 (plain) or 2 (ring)");
@@ -170,7 +170,7 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
         float *XT = nullptr;
         TSG_TRY(ws_acquire(0, (size_t)mtiles * K * 128 * sizeof(float), reinterpret_cast<void **>(&XT)));
         TSG_TRY(transpose_x_tiles(X, XT, M, K));
-        static const int env_ring = getenv("TSG_BCSR_RING") ? atoi(getenv("TSG_BCSR_RING")) : 0;
+        static const int env_ring = getenv("TSG_BCSR_RING") ? atoi(getenv("TSG_BCSR_RING")) : 1;
         if (g_bcsr_kernel == 2 || (g_bcsr_kernel == 0 && env_ring)) {
             int handled = 0;
             const int rc = bcsr_gemm_ring(W, XT, B, a, use_prelu, Y, M, N, K, ldy, &handled);

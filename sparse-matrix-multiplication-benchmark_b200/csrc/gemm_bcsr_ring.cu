@@ -1,17 +1,17 @@
-// gemm_bcsr_ring.cu -- BCSR GEMM with X staged through shared memory (opt-in: TSG_BCSR_RING=1 / tsg_bcsr_set_kernel(2)).
+// gemm_bcsr_ring.cu -- BCSR GEMM with X and W staged through shared memory (the default BCSR kernel; TSG_BCSR_RING=0 or
+// tsg_bcsr_set_kernel(1) selects the plain kernel of gemm_bcsr.cu).
 //
 // Same math and the same sequence of fp32 roundings as k_bcsr_gemm (gemm_bcsr.cu; reference sparse/bcsr.c:141-175):
 // every output starts from its bias and takes one FFMA per stored block element in ascending k.  What changes is where
 // the operands come from.  The plain kernel re-reads a 512-byte row of the X tile from L2 for every block of every
 // block-column (4096^2, 1x8 blocks: 34 GB of L2 reads per call -> L2-bandwidth bound at ~22 % of the FFMA peak).  Here a
 // persistent CTA per SM walks (128 rows of X) x (256 output columns) units like the TCSC kernel does: a producer thread
-// streams kc-row chunks of the K-major X tile AND the matching run of W blocks (local block-rows + values, a private
-// chunk-major copy of the matrix: BStream) into a two-stage shared-memory ring with bulk async copies (TMA engine)
+// streams kc-row chunks of the K-major X tile AND the matching run of W block rows (local k + c values each, a private
+// chunk-major copy of the matrix: BStream; an r x c block is r consecutive entries) into a two-stage shared-memory ring with bulk async copies (TMA engine)
 // completing on mbarriers; 16 compute warps own 16 output columns each (16/c block-columns), lane l holds rows
 // l, l+32, l+64, l+96 -> 64 accumulators per thread.  Per block row: one conflict-free LDS.128 of X, c/4 uniform
 // LDS.128 of values, 4c FFMA -> FFMA-issue bound for c >= 8 instead of L2 bound.
-//
-// Not yet the default: written at the end of round 1 without GPU time left to run the parity suite over it.
+// Measured on B200 (profiles/bcsr_ring_check_r01.json): 4096^3, 1x8 blocks, 50 % sparsity 7.69 -> 3.19 ms, bit-identical.
 #include "tsg_internal.h"
 #include "tsg_ptx.cuh"
 
@@ -25,6 +25,10 @@ constexpr int BR_TN = 256;                        // output columns per unit
 constexpr int BR_CW = BR_TN / BR_NWARP;           // output columns per warp
 constexpr int BR_CNT_BYTES = 256, BR_WSTART_BYTES = 64;
 constexpr size_t BR_SMEM_MAX = 232448;
+#ifndef BR_UNROLL
+#define BR_UNROLL 8
+#endif
+constexpr int BR_UNROLL_N = BR_UNROLL;  // entries of a block-column in flight per warp
 
 // ---- BStream builder ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lower_bound_i32(const int *__restrict__ a, int lo, int hi, int key) {
@@ -39,7 +43,7 @@ __device__ __forceinline__ int lower_bound_i32(const int *__restrict__ a, int lo
 // one CTA per run (tile, chunk), thread t = block-column t of the tile: how many of its blocks fall into the chunk
 // (crow is ascending inside a block-column), their position inside the run, and the run's padded length
 __global__ void __launch_bounds__(256) k_bs_count(const int *__restrict__ cptr, const int *__restrict__ crow, int bc, int tbc, int bpw, int kcb,
-                                                  int nchunk, uint8_t *__restrict__ cnt, uint32_t *__restrict__ colpos,
+                                                  int r, int nchunk, uint8_t *__restrict__ cnt, uint32_t *__restrict__ colpos,
                                                   uint32_t *__restrict__ colsrc, uint32_t *__restrict__ wstart,
                                                   uint32_t *__restrict__ run_total, int *__restrict__ max_run) {
     __shared__ uint32_t wsum[8];
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(256) k_bs_count(const int *__restrict__ cptr, 
     if (t < tbc && col < bc) {
         const int b = __ldg(cptr + col), e = __ldg(cptr + col + 1);
         lo = lower_bound_i32(crow, b, e, chunk * kcb);
-        n = lower_bound_i32(crow, lo, e, (chunk + 1) * kcb) - lo;
+        n = (lower_bound_i32(crow, lo, e, (chunk + 1) * kcb) - lo) * r;  // <= kcb * r <= 224 block rows
     }
     const int lane = t & 31, w = t >> 5;
     uint32_t v = (uint32_t)n;
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256) k_bs_count(const int *__restrict__ cptr, 
 
 // one CTA per run: warp per block-column, lanes copy the column's local block-rows and its values (coalesced writes)
 __global__ void __launch_bounds__(256) k_bs_fill(const int *__restrict__ crow, const int *__restrict__ cblk, const float *__restrict__ values,
-                                                 int rc, int tbc, int kcb, int nchunk, const uint8_t *__restrict__ cnt,
+                                                 int r, int c, int tbc, int kcb, int nchunk, const uint8_t *__restrict__ cnt,
                                                  const uint32_t *__restrict__ colpos, const uint32_t *__restrict__ colsrc,
                                                  const uint32_t *__restrict__ eoff, uint8_t *__restrict__ hdr, float *__restrict__ val) {
     const int run = blockIdx.x, chunk = run % nchunk;
@@ -92,23 +96,26 @@ __global__ void __launch_bounds__(256) k_bs_fill(const int *__restrict__ crow, c
         const int n = cnt[o];
         if (n == 0) continue;
         const uint32_t dst = e0 + colpos[o], src = colsrc[o];
-        for (int i = lane; i < n; i += 32) hdr[dst + i] = (uint8_t)(__ldg(crow + src + i) - chunk * kcb);
-        const int nf = n * rc;
+        for (int i = lane; i < n; i += 32) {  // row of X inside the chunk
+            const int blk = i / r;
+            hdr[dst + i] = (uint8_t)((__ldg(crow + src + blk) - chunk * kcb) * r + (i - blk * r));
+        }
+        const int rc = r * c, nf = n * c;  // a block's r x c values are row-major: r consecutive entries
         for (int q = lane; q < nf; q += 32) {
-            const int i = q / rc, j = q - i * rc;
-            val[(size_t)dst * rc + q] = __ldg(values + (size_t)__ldg(cblk + src + i) * rc + j);
+            const int blk = q / rc, j = q - blk * rc;
+            val[(size_t)dst * c + q] = __ldg(values + (size_t)__ldg(cblk + src + blk) * rc + j);
         }
     }
 }
 
-static size_t ring_stage_bytes(int kcb, int r, int rc, int max_run) {
-    return (size_t)kcb * r * BR_TM * 4 + (size_t)max_run * rc * 4 + (size_t)max_run + BR_CNT_BYTES + BR_WSTART_BYTES;
+static size_t ring_stage_bytes(int kcb, int r, int c, int max_run) {
+    return (size_t)kcb * r * BR_TM * 4 + (size_t)max_run * c * 4 + (size_t)max_run + BR_CNT_BYTES + BR_WSTART_BYTES;
 }
 
 static int build_bstream(tsg_bcsr *W) {
     BStream &bs = W->bs;
     if (bs.built || bs.unsupported) return TSG_OK;
-    const int c = W->c, r = W->r, rc = r * c;
+    const int c = W->c, r = W->r;
     if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 16) || r > 224 || W->br <= 0 || W->bc <= 0) {
         bs.unsupported = true;
         return TSG_OK;
@@ -151,13 +158,13 @@ static int build_bstream(tsg_bcsr *W) {
         TSG_TRY(dev_alloc_t(&max_run_dev, 1));
         TSG_CUDA(cudaMemsetAsync(max_run_dev, 0, sizeof(int), st));
         TSG_CUDA(cudaMemsetAsync(bs.wstart, 0, (size_t)nrun * BR_NWARP * 4, st));
-        k_bs_count<<<nrun, 256, 0, st>>>(W->cptr, W->crow, W->bc, bs.tbc, bpw, kcb, nchunk, bs.cnt, colpos, colsrc, bs.wstart, run_total,
+        k_bs_count<<<nrun, 256, 0, st>>>(W->cptr, W->crow, W->bc, bs.tbc, bpw, kcb, r, nchunk, bs.cnt, colpos, colsrc, bs.wstart, run_total,
                                          max_run_dev);
         TSG_KERNEL_CHECK("k_bs_count");
         int max_run = 0;
         TSG_CUDA(cudaMemcpyAsync(&max_run, max_run_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
         TSG_CUDA(cudaStreamSynchronize(st));
-        if (2 * ring_stage_bytes(kcb, r, rc, max_run) + 64 <= BR_SMEM_MAX) {
+        if (2 * ring_stage_bytes(kcb, r, c, max_run) + 64 <= BR_SMEM_MAX) {
             ok = true;
             bs.kcb = kcb;
             bs.nchunk = nchunk;
@@ -178,10 +185,10 @@ static int build_bstream(tsg_bcsr *W) {
     TSG_CUDA(cudaStreamSynchronize(st));
     bs.entries = h_total;
     TSG_TRY(dev_alloc_t(&bs.hdr, (size_t)h_total + 16));
-    TSG_TRY(dev_alloc_t(&bs.val, ((size_t)h_total + 16) * rc));
+    TSG_TRY(dev_alloc_t(&bs.val, ((size_t)h_total + 16) * c));
     TSG_CUDA(cudaMemsetAsync(bs.hdr, 0, (size_t)h_total + 16, st));
-    TSG_CUDA(cudaMemsetAsync(bs.val, 0, ((size_t)h_total + 16) * rc * sizeof(float), st));
-    k_bs_fill<<<nrun, 256, 0, st>>>(W->crow, W->cblk, W->values, rc, bs.tbc, bs.kcb, bs.nchunk, bs.cnt, colpos, colsrc, bs.eoff, bs.hdr, bs.val);
+    TSG_CUDA(cudaMemsetAsync(bs.val, 0, ((size_t)h_total + 16) * c * sizeof(float), st));
+    k_bs_fill<<<nrun, 256, 0, st>>>(W->crow, W->cblk, W->values, r, c, bs.tbc, bs.kcb, bs.nchunk, bs.cnt, colpos, colsrc, bs.eoff, bs.hdr, bs.val);
     TSG_KERNEL_CHECK("k_bs_fill");
     drop_scratch();
     bs.built = true;
@@ -206,53 +213,48 @@ struct BcsrRingParams {
     uint32_t xstage_bytes, val_stage_bytes, hdr_stage_bytes;
 };
 
-// the blocks of this warp's block-columns inside the staged run, in (block-column, ascending block-row) order
-template <int C, bool R1>
+// the block rows of this warp's block-columns inside the staged run, in (block-column, ascending k) order
+template <int C>
 __device__ __forceinline__ void bcsr_chunk(float (&acc)[BR_CW][4], const float *xs, const float *val_s, const uint8_t *hdr_s,
-                                           const uint8_t *cn, uint32_t ei, int r) {
+                                           const uint8_t *cn, uint32_t ei) {
     constexpr int BPW = BR_CW / C;
 #pragma unroll
     for (int b = 0; b < BPW; ++b) {
         const int n = cn[b];
-#pragma unroll 2
+#pragma unroll BR_UNROLL_N
         for (int t = 0; t < n; ++t, ++ei) {
             const int kl = hdr_s[ei];
-            const int rows = R1 ? 1 : r;
-            const float *xr = xs + (size_t)kl * rows * BR_TM;       // lane's float4 of X row (kl*r + i): rows l, l+32, l+64, l+96
-            const float *wv = val_s + (size_t)ei * rows * C;
-            for (int i = 0; i < rows; ++i, xr += BR_TM, wv += C) {
-                const float4 x = *reinterpret_cast<const float4 *>(xr);
-                float w[C];
-                if constexpr (C >= 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(xs + (size_t)kl * BR_TM);  // rows l, l+32, l+64, l+96 of X row kl
+            const float *wv = val_s + (size_t)ei * C;
+            float w[C];
+            if constexpr (C >= 4) {
 #pragma unroll
-                    for (int q = 0; q < C / 4; ++q) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(wv + 4 * q);
-                        w[(4 * q) % C] = t4.x; w[(4 * q + 1) % C] = t4.y; w[(4 * q + 2) % C] = t4.z; w[(4 * q + 3) % C] = t4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < C; ++j) w[j] = wv[j];
+                for (int q = 0; q < C / 4; ++q) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(wv + 4 * q);
+                    w[(4 * q) % C] = t4.x; w[(4 * q + 1) % C] = t4.y; w[(4 * q + 2) % C] = t4.z; w[(4 * q + 3) % C] = t4.w;
                 }
+            } else {
 #pragma unroll
-                for (int j = 0; j < C; ++j) {  // bcsr.c:160-170: y += x * w, ascending k, one rounding per step
-                    acc[b * C + j][0] = fmaf(x.x, w[j], acc[b * C + j][0]);
-                    acc[b * C + j][1] = fmaf(x.y, w[j], acc[b * C + j][1]);
-                    acc[b * C + j][2] = fmaf(x.z, w[j], acc[b * C + j][2]);
-                    acc[b * C + j][3] = fmaf(x.w, w[j], acc[b * C + j][3]);
-                }
+                for (int j = 0; j < C; ++j) w[j] = wv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < C; ++j) {  // bcsr.c:160-170: y += x * w, ascending k, one rounding per step
+                acc[b * C + j][0] = fmaf(x.x, w[j], acc[b * C + j][0]);
+                acc[b * C + j][1] = fmaf(x.y, w[j], acc[b * C + j][1]);
+                acc[b * C + j][2] = fmaf(x.z, w[j], acc[b * C + j][2]);
+                acc[b * C + j][3] = fmaf(x.w, w[j], acc[b * C + j][3]);
             }
         }
     }
 }
 
-template <int C, bool R1>
+template <int C>
 __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRingParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_bytes = p.xstage_bytes + p.val_stage_bytes + p.hdr_stage_bytes + BR_CNT_BYTES + BR_WSTART_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)stage_bytes);
     uint64_t *empty = full + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rc = p.r * C;
 
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -278,10 +280,10 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
                     const uint32_t e0 = __ldg(p.eoff + run), e1 = __ldg(p.eoff + run + 1), ne = e1 - e0;
                     const int brows = min(p.kcb, p.br - c * p.kcb);
                     const uint32_t xbytes = (uint32_t)brows * p.r * (BR_TM * 4);
-                    mbar_arrive_expect_tx(&full[s], xbytes + ne * (uint32_t)rc * 4u + ne + BR_CNT_BYTES + BR_WSTART_BYTES);
+                    mbar_arrive_expect_tx(&full[s], xbytes + ne * (uint32_t)C * 4u + ne + BR_CNT_BYTES + BR_WSTART_BYTES);
                     bulk_g2s(st, p.XT + ((size_t)mt * p.K + (size_t)c * p.kcb * p.r) * BR_TM, xbytes, &full[s]);
                     if (ne) {
-                        bulk_g2s(st + p.xstage_bytes, p.val + (size_t)e0 * rc, ne * (uint32_t)rc * 4u, &full[s]);
+                        bulk_g2s(st + p.xstage_bytes, p.val + (size_t)e0 * C, ne * (uint32_t)C * 4u, &full[s]);
                         bulk_g2s(st + p.xstage_bytes + p.val_stage_bytes, p.hdr + e0, ne, &full[s]);
                     }
                     bulk_g2s(st + p.xstage_bytes + p.val_stage_bytes + p.hdr_stage_bytes, p.cnt + (size_t)run * 256, BR_CNT_BYTES, &full[s]);
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
             const uint8_t *hdr_s = st + p.xstage_bytes + p.val_stage_bytes;
             const uint8_t *cnt_s = hdr_s + p.hdr_stage_bytes;
             const uint32_t *wstart_s = reinterpret_cast<const uint32_t *>(cnt_s + BR_CNT_BYTES);
-            bcsr_chunk<C, R1>(acc, xs, val_s, hdr_s, cnt_s + warp * BPW, wstart_s[warp], p.r);
+            bcsr_chunk<C>(acc, xs, val_s, hdr_s, cnt_s + warp * BPW, wstart_s[warp]);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
@@ -346,15 +348,15 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
     }
 }
 
-template <int C, bool R1>
+template <int C>
 static int launch_ring(const BcsrRingParams &p, size_t smem_bytes) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        TSG_CUDA(cudaFuncSetAttribute(k_bcsr_gemm_ring<C, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM_MAX));
+        TSG_CUDA(cudaFuncSetAttribute(k_bcsr_gemm_ring<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM_MAX));
         attr_set = true;
     }
     const int grid = p.units < num_sms() ? p.units : num_sms();
-    k_bcsr_gemm_ring<C, R1><<<grid, BR_THREADS, smem_bytes, stream()>>>(p);
+    k_bcsr_gemm_ring<C><<<grid, BR_THREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_bcsr_gemm_ring");
     return TSG_OK;
 }
@@ -373,17 +375,16 @@ int bcsr_gemm_ring(tsg_bcsr *W, const float *XT, const float *B, float a, int us
     p.units = ((M + BR_TM - 1) / BR_TM) * bs.ntile;
     p.a = a; p.use_prelu = use_prelu;
     p.xstage_bytes = (uint32_t)bs.kcb * W->r * BR_TM * 4;
-    p.val_stage_bytes = (uint32_t)bs.max_run * W->r * W->c * 4;
+    p.val_stage_bytes = (uint32_t)bs.max_run * W->c * 4;
     p.hdr_stage_bytes = (uint32_t)bs.max_run;
-    const size_t smem_bytes = 2 * ring_stage_bytes(bs.kcb, W->r, W->r * W->c, bs.max_run) + 64;
-    const bool r1 = (W->r == 1);
+    const size_t smem_bytes = 2 * ring_stage_bytes(bs.kcb, W->r, W->c, bs.max_run) + 64;
     int rc;
     switch (W->c) {
-        case 1: rc = r1 ? launch_ring<1, true>(p, smem_bytes) : launch_ring<1, false>(p, smem_bytes); break;
-        case 2: rc = r1 ? launch_ring<2, true>(p, smem_bytes) : launch_ring<2, false>(p, smem_bytes); break;
-        case 4: rc = r1 ? launch_ring<4, true>(p, smem_bytes) : launch_ring<4, false>(p, smem_bytes); break;
-        case 8: rc = r1 ? launch_ring<8, true>(p, smem_bytes) : launch_ring<8, false>(p, smem_bytes); break;
-        default: rc = r1 ? launch_ring<16, true>(p, smem_bytes) : launch_ring<16, false>(p, smem_bytes); break;
+        case 1: rc = launch_ring<1>(p, smem_bytes); break;
+        case 2: rc = launch_ring<2>(p, smem_bytes); break;
+        case 4: rc = launch_ring<4>(p, smem_bytes); break;
+        case 8: rc = launch_ring<8>(p, smem_bytes); break;
+        default: rc = launch_ring<16>(p, smem_bytes); break;
     }
     if (rc == TSG_OK) *handled = 1;
     return rc;

@@ -81,9 +81,10 @@ struct KStream {
 };
 
 // ---- private chunk-major stream of a BCSR matrix (gemm_bcsr_ring.cu) -------------------------------------------------
-// Run (tile, chunk) = the blocks of one 256-output-column tile whose block-row falls into chunk `chunk` (kcb block-rows),
-// ordered by (block-column, block-row) and padded to a multiple of 16 entries, so that a run's local block-rows (`hdr`,
-// one byte each) and its block values (`val`, r*c floats each) are each ONE contiguous, 16-byte aligned span.
+// An entry is one block ROW (1 x c values at one k), so an r x c block contributes r consecutive entries.  Run (tile,
+// chunk) = the entries of one 256-output-column tile whose k falls into chunk `chunk` (kcb block-rows = kcb*r rows of X),
+// ordered by (block-column, k) and padded to a multiple of 16 entries, so that a run's local k (`hdr`, one byte each)
+// and its values (`val`, c floats each) are each ONE contiguous, 16-byte aligned span.
 struct BStream {
     int kcb = 0;      // block-rows per chunk (kcb * r <= 224 rows of X, kcb <= 255)
     int nchunk = 0;   // ceil(br / kcb)
@@ -92,8 +93,8 @@ struct BStream {
     uint8_t *cnt = nullptr;      // [ntile*nchunk][256]  entries per block-column of the tile
     uint32_t *wstart = nullptr;  // [ntile*nchunk][16]   first entry (relative to the run) of each compute warp
     uint32_t *eoff = nullptr;    // [ntile*nchunk + 1]   first entry of each run
-    uint8_t *hdr = nullptr;      // [entries]            block-row inside the chunk
-    float *val = nullptr;        // [entries][r*c]
+    uint8_t *hdr = nullptr;      // [entries]            row of X inside the chunk (k - chunk*kcb*r)
+    float *val = nullptr;        // [entries][c]
     long long entries = 0;
     int max_run = 0;             // longest run (entries, padded)
     bool built = false, unsupported = false;
