@@ -133,9 +133,18 @@ static int build_bstream(tsg_bcsr *W) {
         max_run_dev = nullptr;
     };
     auto drop_stream = [&]() {
-        dev_free(bs.cnt); dev_free(bs.wstart); dev_free(bs.eoff);
-        bs.cnt = nullptr; bs.wstart = nullptr; bs.eoff = nullptr;
+        dev_free(bs.cnt); dev_free(bs.wstart); dev_free(bs.eoff); dev_free(bs.hdr); dev_free(bs.val);
+        bs.cnt = nullptr; bs.wstart = nullptr; bs.eoff = nullptr; bs.hdr = nullptr; bs.val = nullptr;
     };
+    struct Cleanup {  // any early error return leaves neither scratch nor a half-built stream behind
+        decltype(drop_scratch) &scratch;
+        decltype(drop_stream) &stream;
+        BStream &bs;
+        ~Cleanup() {
+            scratch();
+            if (!bs.built) stream();
+        }
+    } cleanup{drop_scratch, drop_stream, bs};
     // largest chunk whose worst run still fits two stages: try a descending ladder of chunk heights (rows of X)
     const int ladder[8] = {224, 160, 112, 72, 56, 40, 24, 8};
     int nrun = 0, prev_kcb = -1;
@@ -190,7 +199,6 @@ static int build_bstream(tsg_bcsr *W) {
     TSG_CUDA(cudaMemsetAsync(bs.val, 0, ((size_t)h_total + 16) * c * sizeof(float), st));
     k_bs_fill<<<nrun, 256, 0, st>>>(W->crow, W->cblk, W->values, r, c, bs.tbc, bs.kcb, bs.nchunk, bs.cnt, colpos, colsrc, bs.eoff, bs.hdr, bs.val);
     TSG_KERNEL_CHECK("k_bs_fill");
-    drop_scratch();
     bs.built = true;
     return TSG_OK;
 }
