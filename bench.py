@@ -399,7 +399,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc if world == 1 else f"{desc}, {'N=' + str(N) + ' columns split over ' + str(world) + ' GPUs' if strong else 'per GPU: ' + str(world) + ' x ' + str(Ng) + ' = ' + str(N) + ' columns'}, N-sharded, X broadcast from rank 0, "
-                                                            f"Y all-gathered ({['ncclAllGather + re-layout', 'fused NVLink peer stores in the GEMM epilogue', 'copy-engine peer pushes gated by in-kernel progress counters, overlapped with the GEMM', 'fused: output tiles staged in shared memory, TMA bulk stores to the local Y and every peer'][args.dist_mode]})",
+                                                            f"Y all-gathered ({['ncclAllGather + re-layout', 'fused NVLink peer stores in the GEMM epilogue', 'copy-engine peer pushes gated by in-kernel progress counters, overlapped with the GEMM', 'fused: output tiles staged in shared memory, TMA bulk stores to the local Y and every peer', 'fused as mode 3 with a separate output tile (stores of one unit overlap the gathers of the next)'][args.dist_mode]})",
                        "M": M, "K": K, "N": N, "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA,
                        "order": "tcsc_sgemm_prelu_basic (0, +pos asc, -neg asc, +b, PReLU) -- bit-identical to the reference",
                        "l2": f"{len(Xs)} X buffers{'' if len(Ys) == 1 else f' and {len(Ys)} Y buffers'} rotated ({(len(Xs) * M * K + len(Ys) * M * N) * 4 >> 20} MiB > 126 MB L2)",
@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
-    ap.add_argument("--dist-mode", type=int, default=3, choices=[0, 1, 2, 3])
+    ap.add_argument("--dist-mode", type=int, default=3, choices=[0, 1, 2, 3, 4])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

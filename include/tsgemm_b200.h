@@ -152,7 +152,9 @@ int tsg_dist_barrier(tsg_dist *D);
  *         pushes finished row blocks with strided 2-D DMA copies, so the all-gather overlaps the GEMM (M >= 32).
  * mode 3: Y_dev must be the tsg_dist_alloc_y buffer; fused all-gather through the TMA engine: every finished 128-row
  *         tile is staged in shared memory and its row segments are written to the local Y and to every peer's Y with
- *         bulk async stores while the SMs gather the next tile (M >= 32, N and the slab width multiples of 4). */
+ *         bulk async stores while the SMs gather the next tile (M >= 32, N and the slab width multiples of 4).
+ * mode 4: experimental variant of mode 3: the staged tile gets shared memory of its own (shorter K chunks), so the
+ *         stores of one unit drain while the next unit is gathered; same results, not yet measured at N > 1. */
 int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X_dev, int root, const float *B_dev, float a, int use_prelu,
                   int order, float *Y_dev, int M, int N, int K, int mode);
 

@@ -253,19 +253,20 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         return tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
     }
 
-    if (mode == 3) {
+    if (mode == 3 || mode == 4) {
         // (2+3 fused, TMA) the kernel stages every finished 128-row tile in shared memory and the TMA engine writes each
         // row segment (up to 1 KB) to the local Y and to every peer's Y with bulk async stores: NVLink-sized packets
         // (687 GB/s measured, tools/peer_store_bw.py, vs 145 GB/s for mode 1's per-lane stores), issued while the SMs
-        // are already gathering the next tile.
-        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3): Y must be the buffer returned by tsg_dist_alloc_y");
-        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3): Y buffer too small");
-        if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 3) needs M >= %d", TSG_SKINNY_M);
+        // are already gathering the next tile.  Mode 4 (experimental) gives the staged tile shared memory of its own
+        // (shorter K chunks) so that the producer never waits for the stores of the previous unit.
+        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3/4): Y must be the buffer returned by tsg_dist_alloc_y");
+        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 3/4): Y buffer too small");
+        if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 3/4) needs M >= %d", TSG_SKINNY_M);
         float *peers[TSG_MAX_PEERS];
         int np = 0;
         for (int p = 1; p < D->world; ++p) peers[np++] = D->y_peer[(D->rank + p) % D->world] + col0;
         TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y
-        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr, 1));
+        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr, mode == 4 ? 2 : 1));
         return tsg_dist_barrier(D);
     }
 

@@ -65,6 +65,7 @@ struct GemmParams {
     unsigned int *done;
     int ngroups;       // row tiles [gbound[g], gbound[g+1]) form progress group g (at most 8 groups)
     int gbound[9];
+    uint32_t tile_off;  // TILE_SEP instantiation: byte offset of the output tile (behind the stage ring)
 };
 
 // ---- gather-add over one chunk for the columns of a warp ---------------------------------------------------------------
@@ -158,6 +159,9 @@ __host__ __device__ __forceinline__ Unit decode_unit_raw(int units_full, int sub
 }
 __device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) { return decode_unit_raw(p.units_full, p.sub, p.ntiles, u); }
 
+// TILE_SEP (dist mode 4): the staged output tile has shared memory of its own instead of overlaying the stage ring, so the
+// producer never waits for the bulk stores and a unit's stores drain while the next unit is being gathered.
+template <bool TILE_SEP>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_bytes = p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const Unit un = decode_unit(p, u);
                 const int tn = un.cw * NWARP;
                 // fused epilogue: the previous unit's output tile overlays the stage ring until its bulk stores have read it
-                if (p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
+                if (!TILE_SEP && p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
                 const uint32_t woff_copy = (uint32_t)(((tn / 8 + 1) * 4 + 15) & ~15);
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int c = 0; c < p.nchunk; ++c, ++it) {
@@ -260,7 +264,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             }
         }
         // ---- fused epilogue: bias, PReLU, store (and, on the multi-GPU path, the same store into every peer's Y) ----
-        if (p.fused_tma) asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp is done reading the stage ring
+        if constexpr (TILE_SEP) {
+            // the previous unit's bulk stores must have read the tile before it is overwritten
+            if (tid < TM) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+        } else {
+            if (p.fused_tma) asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp is done reading the stage ring
+        }
+        uint8_t *const tile_base = TILE_SEP ? smem + p.tile_off : smem;
         const bool full_vec = vec_ok && (cw % 4 == 0) && (nbase + cw <= p.N);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             if (p.fused_tma) {
                 // stage this lane's cw values of row (lane + 32 v) into the output tile (row pitch 260 words: consecutive
                 // lanes = consecutive rows land 4 banks apart, so each quarter-warp float4 store covers all 32 banks)
-                float *trow = reinterpret_cast<float *>(smem) + (size_t)(lane + 32 * v) * TILE_PITCH + warp * cw;
+                float *trow = reinterpret_cast<float *>(tile_base) + (size_t)(lane + 32 * v) * TILE_PITCH + warp * cw;
 #pragma unroll
                 for (int j = 0; j < CWMAX; j += 4)
                     if (j < cw) *reinterpret_cast<float4 *>(trow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const int m = un.mt * TM + tid;
                 const int ncol = min(cw * NWARP, p.N - un.n0);
                 if (m < p.M && ncol > 0) {
-                    const uint32_t src = smem_addr(reinterpret_cast<float *>(smem) + (size_t)tid * TILE_PITCH);
+                    const uint32_t src = smem_addr(reinterpret_cast<float *>(tile_base) + (size_t)tid * TILE_PITCH);
                     const uint32_t bytes = (uint32_t)ncol * 4u;
                     for (int q = -1; q < p.npeer; ++q) {
                         float *dst = ((q < 0) ? p.Y : p.peerY[q]) + (size_t)m * p.ldy + un.n0;
@@ -318,10 +329,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                     }
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be overwritten again
+                if constexpr (!TILE_SEP) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be overwritten again
             }
-            asm volatile("bar.sync 2, 512;" ::: "memory");
-            if (lane == 0) mbar_arrive(epi);
+            if constexpr (!TILE_SEP) {
+                asm volatile("bar.sync 2, 512;" ::: "memory");
+                if (lane == 0) mbar_arrive(epi);
+            }
         }
         if (p.done) {  // publish: this warp's share of unit (mt, n0) is in memory
             __threadfence_system();
@@ -582,10 +595,11 @@ static void plan_progress(const UnitPlan &u, Progress *prog) {
     }
 }
 
-static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
+static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
@@ -595,7 +609,8 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes) {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream());
     }
-    k_tcsc_gemm<<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    if (tile_sep) k_tcsc_gemm<true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    else k_tcsc_gemm<false><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_tcsc_gemm");
     if (g_profile) {
         cudaEventRecord(e1, stream());
@@ -684,9 +699,9 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     if (N != W->cols || K != W->rows) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: W is %d x %d but K=%d, N=%d", W->rows, W->cols, K, N);
     if (order < 0 || order > 2) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
     if (ldy < N) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: ldy < N");
-    if (!fused_tma && npeer == 0 && !done) {  // TSG_FUSED_EPILOGUE=1: route the single-GPU store through the TMA epilogue too
+    if (!fused_tma && npeer == 0 && !done) {  // TSG_FUSED_EPILOGUE=1|2: route the single-GPU store through the TMA epilogue too (2 = separate tile)
         static const int env_fused = getenv("TSG_FUSED_EPILOGUE") ? atoi(getenv("TSG_FUSED_EPILOGUE")) : 0;
-        if (env_fused && M >= TSG_SKINNY_M && !(N & 3) && !(ldy & 3) && !(reinterpret_cast<uintptr_t>(Y) & 15)) fused_tma = 1;
+        if (env_fused && M >= TSG_SKINNY_M && !(N & 3) && !(ldy & 3) && !(reinterpret_cast<uintptr_t>(Y) & 15)) fused_tma = (env_fused == 2) ? 2 : 1;
     }
     if (fused_tma && ((N & 3) || (ldy & 3) || (reinterpret_cast<uintptr_t>(Y) & 15)))
         return set_error(TSG_EUNSUPPORTED, "fused TMA epilogue needs N, ldy multiples of 4 and a 16-byte aligned Y");
@@ -694,7 +709,9 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     const bool skinny = npeer == 0 && !done && !fused_tma && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
     if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
 
-    TSG_TRY(build_kstream(W));
+    const bool tile_sep = (fused_tma == 2);
+    constexpr int kTileBytes = TM * TILE_PITCH * 4;
+    TSG_TRY(build_kstream(W, tile_sep ? kTileBytes : 0));
     const KStream &ks = W->ks;
     GemmParams p;
     p.mtiles = (M + TM - 1) / TM;
@@ -709,9 +726,11 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
     size_t ring_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES);
-    if (fused_tma && ring_bytes < (size_t)TM * TILE_PITCH * 4) ring_bytes = (size_t)TM * TILE_PITCH * 4;  // tiny K: the tile is the larger one
-    p.bar_off = (uint32_t)ring_bytes;
-    const size_t smem_bytes = ring_bytes + 64;
+    if (fused_tma == 1 && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
+    p.tile_off = tile_sep ? (uint32_t)ring_bytes : 0u;
+    p.bar_off = (uint32_t)(tile_sep ? ring_bytes + kTileBytes : ring_bytes);
+    const size_t smem_bytes = (size_t)p.bar_off + 64;
+    if (smem_bytes > 232448) return set_error(TSG_EUNSUPPORTED, "tsg_tcsc_gemm: the gather stream of this matrix leaves no room for a separate output tile");
     const UnitPlan up = plan_units(M, N, num_sms());
     p.ntiles = up.ntiles;
     p.units_full = up.units_full;
@@ -726,7 +745,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         p.ngroups = prog->ngroups;
         for (int i = 0; i <= prog->ngroups; ++i) p.gbound[i] = prog->gbound[i];
     }
-    int rc = launch_tiled(p, smem_bytes);
+    int rc = launch_tiled(p, smem_bytes, tile_sep);
     int rc2 = ws_release(0);
     return rc ? rc : rc2;
 }

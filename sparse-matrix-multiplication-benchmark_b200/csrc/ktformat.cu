@@ -100,11 +100,18 @@ static void free_kstream(KStream &ks) {
 }
 
 // shared-memory budget of the GEMM kernel (gemm_tcsc.cu): two pipeline stages must fit 227 KB
-static constexpr long long kSmemBudget = 232448 - 1024;
+static constexpr long long kSmemTotal = 232448 - 1024;
 static long long stage_bytes_for(int kc, int tile_words) { return (long long)kc * 512 + (long long)tile_words * 4 + 256 + 160; }
 
-int build_kstream(tsg_tcsc *W) {
-    if (W->ks.built) return TSG_OK;
+int build_kstream(tsg_tcsc *W, int smem_reserved) {
+    // smem_reserved: shared memory the kernel keeps for something else (the separate output tile of dist mode 4); the
+    // chunk height is part of the stream's layout, so a different reservation means a different stream
+    if (W->ks.built && W->ks.smem_reserved == smem_reserved) return TSG_OK;
+    if (W->ks.built) {
+        free_kstream(W->ks);
+        W->ks = KStream();
+    }
+    const long long kSmemBudget = kSmemTotal - smem_reserved;
     cudaStream_t st = stream();
     const int K = W->rows, N = W->cols;
     const long long nnz = (long long)W->n_pos + W->n_neg;
@@ -119,6 +126,7 @@ int build_kstream(tsg_tcsc *W) {
     if (kc > K) kc = (K > 0) ? K : 1;
     for (int attempt = 0; attempt < 12; ++attempt) {
         KStream ks;
+        ks.smem_reserved = smem_reserved;
         ks.kc = kc;
         ks.nchunk = (K + kc - 1) / kc;
         if (ks.nchunk < 1) ks.nchunk = 1;

@@ -77,6 +77,7 @@ struct KStream {
     uint32_t *body = nullptr;  // packed words
     long long body_words = 0;  // capacity
     int max_tile_words = 0;    // max over planes and 256-column tiles of the tile's body words
+    int smem_reserved = 0;     // shared memory left out of the two-stage budget when kc was chosen (0 = the whole 227 KB)
     bool built = false;
 };
 
@@ -126,7 +127,7 @@ namespace tsg {
 int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t *total_dev);
 // classify a pointer: 1 device (or managed), 0 host
 int is_device_pointer(const void *p);
-int build_kstream(tsg_tcsc *W);
+int build_kstream(tsg_tcsc *W, int smem_reserved = 0);
 int bcsr_build_cols(tsg_bcsr *W);
 // ring kernel for BCSR (gemm_bcsr_ring.cu): *handled = 0 when the matrix does not fit its limits (caller falls back
 // to the plain kernel); XT = K-major 128-row tiles of X
@@ -138,7 +139,9 @@ struct Progress {
     int gbound[9] = {0};
     unsigned int target[8] = {0};
 };
-// tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu)
+// tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu);
+// fused_tma: 0 = per-lane stores, 1 = TMA bulk stores from a tile that overlays the stage ring, 2 = TMA bulk stores from
+// a tile of its own (shorter chunks, but the stores of one unit overlap the gathers of the next)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                     long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma = 0);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)

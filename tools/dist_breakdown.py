@@ -48,7 +48,7 @@ res["torch_bcast_X_64MB"] = timeit(lambda: dist.broadcast(X, src=0))
 res["tsg_barrier"] = timeit(lambda: D.barrier())
 Bl = B[c0:c0 + nc].contiguous()
 res["local_gemm_only(world=1 path)"] = timeit(lambda: t.lib().tsg_tcsc_gemm(W.h, t._ptr(X), t._ptr(Bl), 0.2, 1, 1, Y.data_ptr() + 4 * c0, M, nc, K, N))
-for mode in (3, 2, 1, 0):
+for mode in (4, 3, 2, 1, 0):
     Yb = Y if mode else torch.empty((M, N), device="cuda")
     res[f"dist_gemm_mode{mode}_nobcast"] = timeit(lambda: D.gemm(W, X, B, Yb, N, a=0.2, use_prelu=True, root=-1, mode=mode))
     res[f"dist_gemm_mode{mode}_bcast"] = timeit(lambda: D.gemm(W, X, B, Yb, N, a=0.2, use_prelu=True, root=0, mode=mode))
