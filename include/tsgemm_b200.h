@@ -115,6 +115,12 @@ int tsg_gen_ternary_f32(float *W_dev, long long n, uint64_t seed, uint32_t num, 
 int tsg_gen_ternary_i32(int *W_dev, long long n, uint64_t seed, uint32_t num, uint32_t den);
 int tsg_gen_uniform_f32(float *X_dev, long long n, uint64_t seed);
 int tsg_gen_intvalued_f32(float *X_dev, long long n, uint64_t seed, int range);
+/* the two patterns of generateSparseMatrix (reference SparseGEMM.h:53-102) as counter-based generators, H x W row-major:
+ * uniform != 0: every window of 2*nonZero columns of every row holds one +1 and one -1 on distinct even offsets
+ * (nonZero >= 2); uniform == 0: row h holds (W/nonZero)/2 + d(h) entries +1 and (W/nonZero)/2 - d(h) entries -1 at
+ * distinct random columns, d(h) uniform on [0, W/nonZero/20 + 1] (W <= 2^20). */
+int tsg_gen_sparse_pattern_i32(int *W_dev, int H, int W, int nonZero, int uniform, uint64_t seed);
+int tsg_gen_sparse_pattern_f32(float *W_dev, int H, int W, int nonZero, int uniform, uint64_t seed);
 /* ternary generator for a column slice [col0, col0+ncols) of a K x N matrix (values identical to the full matrix) */
 int tsg_gen_ternary_slice_f32(float *W_dev, int K, int N, int col0, int ncols, uint64_t seed, uint32_t num, uint32_t den);
 /* fp64-accumulating dense check on the device: out[0] = max |Y - y64| / max(|y64|,1), out[1] = max |Y - y64|,

@@ -116,6 +116,7 @@ class Port:
         L.orc_gen_ternary_i32.argtypes = [_i32p, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_gen_uniform_f32.argtypes = [_f32p, C.c_int64, C.c_uint64]
         L.orc_gen_intvalued_f32.argtypes = [_f32p, C.c_int64, C.c_uint64, i]
+        L.orc_gen_sparse_pattern_i32.argtypes = [_i32p, i, i, i, i, C.c_uint64]
         L.orc_time_tcsc_sgemm_prelu_basic.argtypes = tc + [f, _f32p, i, i, i, i]
         L.orc_time_tcsc_sgemm_prelu_basic.restype = d
 
@@ -255,6 +256,13 @@ class Port:
         X = np.empty(shape, np.float32)
         self.lib.orc_gen_intvalued_f32(X, X.size, seed, rng)
         return X
+
+    def gen_sparse_pattern(self, H, W, non_zero, uniform, seed):
+        """generateSparseMatrix<int> (SparseGEMM.h:53-102) with counter-based draws; int32 H x W"""
+        out = np.empty((H, W), np.int32)
+        if self.lib.orc_gen_sparse_pattern_i32(out, H, W, non_zero, int(bool(uniform)), seed) != 0:
+            raise ValueError("gen_sparse_pattern: bad arguments")
+        return out
 
     def time_prelu_basic(self, X, W: Tcsc, B, a, reps=1):
         X, B = _as_f32(X), _as_f32(B)

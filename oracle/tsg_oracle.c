@@ -10,6 +10,8 @@
 
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 /* ============================================================================================================
@@ -389,6 +391,47 @@ void orc_gen_uniform_f32(float *X, int64_t n, uint64_t seed) {
         uint32_t m24 = (uint32_t)(orc_hash64(seed, (uint64_t)i) >> 40); /* 24 random bits */
         X[i] = (float)m24 * (1.0f / 8388608.0f) - 1.0f;                 /* exact: (m24 - 2^23) * 2^-23 */
     }
+}
+
+/* generateSparseMatrix patterns (SparseGEMM.h:53-102).  Written independently of the product's gen_pattern.h: the skewed
+ * pattern sorts the row's selection keys instead of bisecting for thresholds. */
+static uint32_t below(uint64_t h, uint32_t n) { return (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * n) >> 32); }
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return (x > y) - (x < y);
+}
+int orc_gen_sparse_pattern_i32(int *Wm, int H, int W, int nonZero, int uniform, uint64_t seed) {
+    if (!Wm || H < 0 || W < 0 || nonZero < 1 || (uniform && nonZero < 2) || (!uniform && W > (1 << 20))) return -1;
+    memset(Wm, 0, (size_t)H * (size_t)W * sizeof(int));
+    if (uniform) { /* SparseGEMM.h:56-68 */
+        int window = 2 * nonZero, nwin = (W + window - 1) / window;
+        for (int h = 0; h < H; ++h)
+            for (int g = 0; g < nwin; ++g) {
+                uint64_t cell = ((uint64_t)h * (uint64_t)nwin + (uint64_t)g) * 2u;
+                uint32_t plus = below(orc_hash64(seed, cell), (uint32_t)nonZero);
+                uint32_t minus = below(orc_hash64(seed, cell + 1u), (uint32_t)nonZero - 1u);
+                if (minus >= plus) ++minus; /* the reference redraws until the two slots differ (:62-64) */
+                int wp = g * window + 2 * (int)plus, wm = g * window + 2 * (int)minus;
+                if (wp < W) Wm[(size_t)h * W + wp] = 1; /* the reference writes past the row end here (:61,65) */
+                if (wm < W) Wm[(size_t)h * W + wm] = -1;
+            }
+        return 0;
+    }
+    uint64_t *keys = (uint64_t *)malloc((size_t)(W > 0 ? W : 1) * sizeof(uint64_t));
+    if (!keys) return -1;
+    for (int h = 0; h < H; ++h) { /* SparseGEMM.h:74-98 */
+        int per_row = W / nonZero, half = per_row / 2, dmax = per_row / 20 + 1;
+        int d = (int)below(orc_hash64(seed + 0x632BE59BD9B4E019ull, (uint64_t)h), (uint32_t)dmax + 1u);
+        int n_plus = half + d, n_minus = half - d;
+        if (n_minus < 0) n_minus = 0;
+        if (n_plus > W) n_plus = W;
+        if (n_minus > W - n_plus) n_minus = W - n_plus;
+        for (int w = 0; w < W; ++w) keys[w] = (orc_hash64(seed, (uint64_t)h * (uint64_t)W + (uint64_t)w) & ~0xFFFFFull) | (uint64_t)w;
+        qsort(keys, (size_t)W, sizeof(uint64_t), cmp_u64);
+        for (int i = 0; i < n_plus + n_minus; ++i) Wm[(size_t)h * W + (int)(keys[i] & 0xFFFFFull)] = (i < n_plus) ? 1 : -1;
+    }
+    free(keys);
+    return 0;
 }
 
 void orc_gen_intvalued_f32(float *X, int64_t n, uint64_t seed, int range) {

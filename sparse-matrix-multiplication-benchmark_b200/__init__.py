@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.tsg_gen_ternary_i32.argtypes = [vp, ll, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_ternary_slice_f32.argtypes = [vp, i, i, i, i, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_uniform_f32.argtypes = [vp, ll, C.c_uint64]
+    L.tsg_gen_sparse_pattern_i32.argtypes = [vp, i, i, i, i, C.c_uint64]
+    L.tsg_gen_sparse_pattern_f32.argtypes = [vp, i, i, i, i, C.c_uint64]
     L.tsg_gen_intvalued_f32.argtypes = [vp, ll, C.c_uint64, i]
     L.tsg_verify_dense_f64.argtypes = [vp, vp, vp, f, i, vp, i, i, i, ll, i, i, C.POINTER(C.c_double * 2)]
     L.tsg_dist_unique_id.argtypes = [C.POINTER(C.c_ubyte * 128)]
@@ -468,6 +470,17 @@ def gen_ternary_slice(K, N, col0, ncols, seed, num, den, device="cuda"):
     W = torch.empty((K, ncols), dtype=torch.float32, device=device)
     _check(lib().tsg_gen_ternary_slice_f32(_ptr(W), K, N, col0, ncols, seed, num, den), "tsg_gen_ternary_slice")
     return W
+
+
+def gen_sparse_pattern(H, W, non_zero, uniform, seed, device="cuda", dtype=None):
+    """generateSparseMatrix (reference SparseGEMM.h:53-102) on the device: the window pattern (uniform=True) or the
+    row-skewed pattern (uniform=False); int32 (what SparseFormat takes) or float32."""
+    import torch
+    dtype = dtype or torch.int32
+    out = torch.empty((H, W), device=device, dtype=dtype)
+    fn = lib().tsg_gen_sparse_pattern_i32 if dtype == torch.int32 else lib().tsg_gen_sparse_pattern_f32
+    _check(fn(_ptr(out), H, W, int(non_zero), int(bool(uniform)), seed), "tsg_gen_sparse_pattern")
+    return out
 
 
 def gen_uniform(shape, seed, device="cuda"):

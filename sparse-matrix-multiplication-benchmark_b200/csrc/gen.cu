@@ -5,6 +5,7 @@
 // Distributions follow the reference's rands_sparse / rands_dense (dense/utils.h:9-68) and initX
 // (SparseGEMM.h:43-50); the reference itself never seeds (std::random_device / time(0)).
 #include "tsg_internal.h"
+#include "gen_pattern.h"
 
 namespace tsg {
 
@@ -72,6 +73,42 @@ __global__ void k_verify_dense(const float *__restrict__ X, const float *__restr
     }
 }
 
+// generateSparseMatrix patterns (gen_pattern.h).  Window pattern: one thread per element.
+template <typename T>
+__global__ void k_gen_window(T *Wm, int H, int Wd, int nonZero, uint64_t seed) {
+    const long long n = (long long)H * Wd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(i / Wd), w = (int)(i - (long long)h * Wd);
+        Wm[i] = (T)gp_window_value(seed, h, w, Wd, nonZero);
+    }
+}
+// Skewed pattern: one warp per row; the two selection thresholds by bisection over the 64-bit key space, the count of
+// keys below the probe spread over the lanes
+__device__ __forceinline__ uint64_t kth_key_warp(uint64_t seed, int h, int Wd, int L, int lane) {
+    uint64_t lo = 0, hi = ~0ull;
+    while (lo < hi) {  // warp-uniform: every lane sees the same count
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int w = lane; w < Wd; w += 32) c += (gp_key(seed, h, w, Wd) <= mid);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= L) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+template <typename T>
+__global__ void __launch_bounds__(128) k_gen_skewed(T *Wm, int H, int Wd, int nonZero, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const int h = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (h >= H) return;  // whole warps leave together
+    int n_plus, n_minus;
+    gp_row_limits(seed, h, Wd, nonZero, &n_plus, &n_minus);
+    const uint64_t t_plus = n_plus > 0 ? kth_key_warp(seed, h, Wd, n_plus, lane) : 0ull;
+    const uint64_t t_all = n_plus + n_minus > 0 ? kth_key_warp(seed, h, Wd, n_plus + n_minus, lane) : 0ull;
+    for (int w = lane; w < Wd; w += 32)
+        Wm[(size_t)h * Wd + w] = (T)gp_skew_value(gp_key(seed, h, w, Wd), n_plus, n_minus, t_plus, t_all);
+}
+
 static int grid_for(long long n) {
     long long g = (n + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
@@ -81,6 +118,23 @@ static int grid_for(long long n) {
 }  // namespace tsg
 
 using namespace tsg;
+
+template <typename T>
+static int gen_sparse_pattern(T *Wm, int H, int Wd, int nonZero, int uniform, uint64_t seed) {
+    TSG_TRY(ensure_device());
+    if (!Wm || H < 0 || Wd < 0 || nonZero < 1) return set_error(TSG_EINVAL, "tsg_gen_sparse_pattern: bad arguments");
+    if (uniform && nonZero < 2) return set_error(TSG_EINVAL, "tsg_gen_sparse_pattern: the window pattern needs nonZero >= 2 (the reference loops forever at 1)");
+    if (!uniform && Wd > (1 << 20)) return set_error(TSG_EUNSUPPORTED, "tsg_gen_sparse_pattern: the skewed pattern supports W <= 2^20");
+    if (H == 0 || Wd == 0) return TSG_OK;
+    if (uniform) {
+        k_gen_window<T><<<grid_for((long long)H * Wd), 256, 0, stream()>>>(Wm, H, Wd, nonZero, seed);
+        TSG_KERNEL_CHECK("k_gen_window");
+    } else {
+        k_gen_skewed<T><<<(unsigned)((H + 3) / 4), 128, 0, stream()>>>(Wm, H, Wd, nonZero, seed);
+        TSG_KERNEL_CHECK("k_gen_skewed");
+    }
+    return TSG_OK;
+}
 
 extern "C" {
 
@@ -113,6 +167,13 @@ int tsg_gen_intvalued_f32(float *X, long long n, uint64_t seed, int range) {
     k_gen_intvalued<<<grid_for(n), 256, 0, stream()>>>(X, n, seed, range);
     TSG_KERNEL_CHECK("k_gen_intvalued");
     return TSG_OK;
+}
+
+int tsg_gen_sparse_pattern_i32(int *W, int H, int Wd, int nonZero, int uniform, uint64_t seed) {
+    return gen_sparse_pattern<int>(W, H, Wd, nonZero, uniform, seed);
+}
+int tsg_gen_sparse_pattern_f32(float *W, int H, int Wd, int nonZero, int uniform, uint64_t seed) {
+    return gen_sparse_pattern<float>(W, H, Wd, nonZero, uniform, seed);
 }
 
 int tsg_verify_dense_f64(const float *X, const float *Wd, const float *B, float a, int use_prelu, const float *Y, int M, int N, int K,
