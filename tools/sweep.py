@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--Ms", default="1,2,4,8,16,32,64,128,256,512,1024,2048,4096,8192")
     ap.add_argument("--dens", default="2,4,10,20,100")
     ap.add_argument("--bcsr", action="store_true")
+    ap.add_argument("--pattern", default="iid", choices=["iid", "window", "skewed"],
+                    help="W generator: iid ternary (rands_sparse), or generateSparseMatrix's window / row-skewed pattern (SparseGEMM.h:53-102)")
     a = ap.parse_args()
     t = ge.load()
     L = t.lib()
@@ -42,7 +44,10 @@ def main():
     peak = 148 * 128 * 1.965e9
     print("format,sparsity,M,K,N,nnz,ms,gadd_per_s,gflops_equiv,frac_fp32_add_peak,frac_smem_ceiling,alg_GBps,kernel")
     for den in [int(x) for x in a.dens.split(",")]:
-        Wd = t.gen_ternary(K, N, 42, 1, den)
+        if a.pattern == "iid":
+            Wd = t.gen_ternary(K, N, 42, 1, den)
+        else:  # den = nonZero of generateSparseMatrix: density 1/den like the iid case
+            Wd = t.gen_sparse_pattern(K, N, den, a.pattern == "window", 42, dtype=torch.float32)
         t_conv = timed(lambda: t.DeviceTcsc.from_dense(Wd).destroy(), 3)
         W = t.DeviceTcsc.from_dense(Wd)
         info = W.stream_info()
