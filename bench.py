@@ -21,8 +21,12 @@ N > 1   the column-partitioned path of north_star (3), weak scaling: every GPU o
           bandwidth of MEASURED_PEAKS.json) and the shared-memory gather ceiling are reported next to it.
 `cpu_baseline` the unmodified reference (oracle/_ref, kind "reference"; else the oracle port) timed on this box's host
           cores on a bounded row sample of the same workload.
---impl reference   times the reference's own CPU implementation of the path (single thread -- sparse/tcsc.c has no
-          threading) on bounded row samples of the same workload and prints the same line with "impl": "reference".
+          `cores` = 1: tcsc_sgemm_prelu_basic has no threading and north_star names the single-threaded build; the
+          reference's OpenMP form on all host threads is reported beside it as `all_threads`.
+--impl reference   times the reference's own CPU implementation of the path with all the host threads it can use:
+          sparseGEMM_PReLU<float> (SparseGEMM.h:151-168, omp parallel for over m) from the -fopenmp build of the
+          unmodified reference (--ref-threads 1: tcsc_sgemm_prelu_basic on one pinned core), on bounded row samples of
+          the same workload; prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -30,6 +34,7 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -153,37 +158,82 @@ def cpu_time_rows(backend, W, rows, K, N, port):
     return backend.time_prelu_basic(X, W, B, ALPHA, reps=1)
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def omp_reference_runs():
+    """The OpenMP build of the reference loads and runs on this host (probed in a subprocess, like the native build)."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available("omp"):
+        return False
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; from oracle.pyoracle import Ref; r = Ref('omp');"
+            "W = r.tcsc_from_dense(np.eye(64, dtype=np.float32)); r.time_sparse_gemm_prelu(np.ones((8, 64), np.float32), W, np.zeros(64, np.float32), 0.2)"
+            ) % ROOT
+    try:
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, timeout=120).returncode == 0
+    except Exception:
+        return False
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path with all the host threads it can use: sparseGEMM_PReLU<float>
+    (SparseGEMM.h:151-168, `#pragma omp parallel for` over m) from the -fopenmp build of the unmodified reference; where that
+    build is absent, tcsc_sgemm_prelu_basic (sparse/tcsc.c:143-165), which has no threading, on one pinned core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from oracle import pyoracle
     from oracle.pyoracle import Port
     port = Port()
     M, K, Ng, num, den, desc = WORKLOADS[args.workload]
     N = Ng if args.workload in STRONG else Ng * max(1, args.gpus)
-    backend, kind, flags = cpu_reference_backend()
-    pin_one_core()  # one thread pinned to one core, as benchmark.sh:36 does
+    threads = 1 if args.ref_threads == 1 else host_threads()
+    use_omp = threads > 1 and omp_reference_runs()
+    if use_omp:
+        os.environ["OMP_NUM_THREADS"] = str(threads)  # read by libgomp when the library is loaded below
+        os.environ.setdefault("OMP_PROC_BIND", "true")
+        backend = pyoracle.Ref("omp")
+        kind, flags = "reference", backend.build_flags
+        threads = backend.omp_max_threads()
+        function = "sparseGEMM_PReLU<float> (SparseGEMM.h:151-168, omp parallel for over m)"
+        timer = backend.time_sparse_gemm_prelu
+    else:
+        backend, kind, flags = cpu_reference_backend()
+        threads = 1
+        pin_one_core()  # one thread pinned to one core, as benchmark.sh:36 does
+        function = "tcsc_sgemm_prelu_basic (sparse/tcsc.c:143-165)"
+        timer = backend.time_prelu_basic
     Wd = port.gen_ternary(K, N, SEED_W, num, den)
     W = backend.tcsc_from_dense(Wd)
     nnz = W.nnz
-    # bounded sample per step so that (steps + warmup) steps end within ~2 minutes
+    B = port.gen_uniform((N,), SEED_B)
+    # bounded sample per step so that (steps + warmup) steps end within ~2 minutes: probe, then scale the row count
     per_step = max(0.5, min(6.0, 110.0 / max(1, args.steps + args.warmup)))
-    rows = cpu_pick_rows(backend, W, M, K, N, per_step, port)
+    probe = min(M, 8 * threads)
+    t_probe = timer(port.gen_uniform((probe, K), SEED_X), W, B, ALPHA, reps=2)
+    rows = min(M, int(max(probe, per_step / max(t_probe / probe, 1e-9))))
+    X = port.gen_uniform((rows, K), SEED_X)  # counter-based generator: rows 0..rows-1 of the workload's X
     secs_list = []
     for i in range(args.warmup + args.steps):
-        secs = cpu_time_rows(backend, W, rows, K, N, port)
+        secs = timer(X, W, B, ALPHA, reps=1)
         if i >= args.warmup:
             secs_list.append(secs)
     mean_s = sum(secs_list) / len(secs_list)
     value = flops_equiv(rows, N, nnz) / mean_s / 1e9
-    sample = f"rows 0..{rows - 1} of {M} (all {N} columns, K={K}), one call per step, 1 thread pinned; the m-outer loop nest is linear in M"
+    sample = (f"rows 0..{rows - 1} of {M} (all {N} columns, K={K}), one call per step, {threads} thread(s)"
+              + ("" if use_omp else " pinned") + "; the m-outer loop nest is linear in M")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc if args.gpus <= 1 else f"{desc}; N scaled to {N} columns for {args.gpus} GPUs", "M": M, "K": K, "N": N,
-                   "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA, "function": "tcsc_sgemm_prelu_basic (sparse/tcsc.c:143-165)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "build": flags,
-                         "host_cores_available": os.cpu_count()},
+                   "sparsity": 1 - num / den, "nnz": nnz, "alpha": ALPHA, "function": function},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "build": flags,
+                         "host_cores_available": os.cpu_count(),
+                         "seconds_for_full_M_extrapolated": mean_s * M / rows},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -385,6 +435,17 @@ def run_ours(args):
         from oracle.pyoracle import Port
         backend, kind, flags = cpu_reference_backend()
         port = Port()
+        # the reference's multi-threaded form (sparseGEMM_PReLU<float>, OpenMP over m) on all host threads: a separate
+        # process (its own OpenMP runtime and CPU affinity), i.e. exactly what `--impl reference` prints
+        all_threads = None
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+                                  "--warmup", "3"], capture_output=True, text=True, timeout=600)
+            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+            all_threads = {"value": ref_line["value"], "unit": UNIT, "cores": ref_line["cpu_baseline"]["cores"],
+                           "function": ref_line["config"]["function"], "sample": ref_line["cpu_baseline"]["sample"]}
+        except Exception as e:  # reported, never fatal: the single-thread figure below is the north-star baseline
+            all_threads = {"unavailable": str(e)[:200]}
         pin_one_core()
         Wc = backend.tcsc_from_dense(Wd_host)
         nnz_c = Wc.nnz
@@ -392,7 +453,8 @@ def run_ours(args):
         secs = cpu_time_rows(backend, Wc, rows, K, N, port)
         cpu_baseline = {"value": flops_equiv(rows, N, nnz_c) / secs / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                         "sample": f"rows 0..{rows - 1} of {M} (all {N} columns), 1 call, {secs:.2f} s, 1 thread pinned (benchmark.sh:36)",
-                        "build": flags, "host_cores_available": os.cpu_count(), "seconds_for_full_M_extrapolated": secs * M / rows}
+                        "build": flags, "host_cores_available": os.cpu_count(), "seconds_for_full_M_extrapolated": secs * M / rows,
+                        "all_threads": all_threads}
 
     if rank == 0:
         line = {
@@ -429,6 +491,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--dist-mode", type=int, default=3, choices=[0, 1, 2, 3, 4])
+    ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: 0 = all host threads (OpenMP build of the reference), 1 = one pinned thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

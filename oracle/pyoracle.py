@@ -275,7 +275,7 @@ class Port:
 # Ref: the unmodified reference
 # =====================================================================================================================
 def ref_path(variant: str = "") -> str:
-    suffix = {"": "", "fm": "_fm", "native": "_native"}[variant]
+    suffix = {"": "", "fm": "_fm", "native": "_native", "omp": "_omp"}[variant]
     return os.path.join(HERE, "_ref", f"libref_oracle{suffix}.so")
 
 
@@ -516,6 +516,22 @@ class Ref:
         M, K = X.shape
         Y = np.empty((M, W.cols), np.float32)
         return float(self.lib.ref_time_tcsc_sgemm_prelu_basic(X, self._handle(W), B, float(a), Y, M, W.cols, K, reps))
+
+    def omp_max_threads(self) -> int:
+        return int(self.lib.ref_omp_max_threads())
+
+    def time_sparse_gemm_prelu(self, X, W, B, a, reps=1):
+        """seconds of sparseGEMM_PReLU<float> (SparseGEMM.h:151-168; `omp parallel for` over m in the omp variant)"""
+        X, B = _as_f32(X), _as_f32(B)
+        M, K = X.shape
+        Y = np.empty((M, W.cols), np.float32)
+        csp, csn, rip, rin = W.arrays()
+        self.lib.ref_time_sparseGEMM_PReLU_f32.restype = C.c_double
+        self.lib.ref_time_sparseGEMM_PReLU_f32.argtypes = [_f32p, _i32p, _i32p, _i32p, _i32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+                                                         C.c_float, C.c_int]
+        rip = rip if rip.size else np.zeros(1, np.int32)
+        rin = rin if rin.size else np.zeros(1, np.int32)
+        return float(self.lib.ref_time_sparseGEMM_PReLU_f32(X, csp, csn, rip, rin, B, Y, M, W.cols, K, float(a), reps))
 
 
 def _aligned_empty(shape, dtype=np.float32, align=32):

@@ -10,6 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "dense/dense.h"
 #include "sparse/tcsc.h"
@@ -116,6 +119,28 @@ double ref_time_tcsc_sgemm_prelu_basic(float *X, const void *W, float *B, float 
         if (s < best) best = s;
     }
     return best;
+}
+
+// the reference's multi-threaded form of the same math: sparseGEMM_PReLU<float> carries `#pragma omp parallel for` over m
+// (SparseGEMM.h:151-168); only the _omp build of this wrapper (-fopenmp) runs it on more than one thread
+double ref_time_sparseGEMM_PReLU_f32(float *X, int *csp, int *csn, int *rip, int *rin, float *b, float *Y, int M, int N, int K, float a,
+                                     int reps) {
+    double best = 1e300;
+    for (int r = 0; r < reps; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        sparseGEMM_PReLU<float>(X, csp, csn, rip, rin, b, Y, M, N, K, a);
+        auto t1 = std::chrono::steady_clock::now();
+        double s = std::chrono::duration<double>(t1 - t0).count();
+        if (s < best) best = s;
+    }
+    return best;
+}
+int ref_omp_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 
 const char *ref_build_flags(void) {

@@ -18,9 +18,19 @@ def test_reference_arm_line_has_the_contract_keys():
     for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if d["cpu_baseline"]["cores"] > 1:  # all host threads: only the reference's OpenMP form of the path can use them
+        assert "omp" in d["config"]["function"] and "-fopenmp" in d["cpu_baseline"]["build"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["value"] > 0 and "workload" in d["config"]
+
+
+def test_reference_arm_single_thread_option():
+    out = subprocess.run([sys.executable, os.path.join(ge.ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "1",
+                          "--ref-threads", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == 1 and "tcsc_sgemm_prelu_basic" in d["config"]["function"]
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

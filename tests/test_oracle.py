@@ -167,3 +167,20 @@ def test_live_reference_crosscheck(port, ref, shape):
     for fn in ("tcsc_sgemm_prelu_basic", "tcsc_sgemm_prelu_optimized_separate", "tcsc_sgemm_prelu_optimized_onthego"):
         assert np.array_equal(getattr(port, fn)(X, w, B, 0.2), getattr(ref, fn)(X, wr, B, 0.2)), fn
     assert ref.compare(port.tcsc_sgemm_basic(X, w, B), ref.gemm_basic(X, Wd, B))  # main.cpp:317
+
+
+def test_openmp_build_of_the_reference_gives_the_same_bits(port, ref):
+    """bench.py --impl reference times sparseGEMM_PReLU<float> from the -fopenmp build (SparseGEMM.h:151-168 parallelises
+    over m, so each output keeps its summation order): same bits as the single-threaded build and as the oracle port"""
+    from oracle.pyoracle import Ref, ref_available
+    if not ref_available("omp"):
+        pytest.skip("oracle/_ref/libref_oracle_omp.so not built (no OpenMP-capable g++)")
+    omp = Ref("omp")
+    assert omp.omp_max_threads() >= 1 and "-fopenmp" in omp.build_flags
+    Wd = port.gen_ternary(256, 192, 5, 1, 4)
+    X, b = port.gen_uniform((67, 256), 6), port.gen_uniform((192,), 7)
+    W = port.tcsc_from_dense(Wd)
+    want = ref.sparse_gemm_prelu(X, W, b, 0.2)
+    assert np.array_equal(omp.sparse_gemm_prelu(X, W, b, 0.2), want)
+    assert np.array_equal(port.sparse_gemm_prelu(X, W, b, 0.2), want)
+    assert omp.time_sparse_gemm_prelu(X, W, b, 0.2, reps=1) > 0
