@@ -60,6 +60,11 @@ void tcsc_sgemm_prelu_optimized_onthego(const dense_t X, const tcsc_t *W, const 
 /* reference sparse/tcsc.h:48, sparse/tcsc.c:167-175; NULL-safe; also drops the cached device mirror of W */
 void tcsc_free(tcsc_t *W);
 
+/* extension: forget the device mirror cached for W.  The library notices a struct that was freed, rebuilt or edited
+ * through W's dimensions, array pointers and a sampled content hash (TSG_MIRROR_CHECK=full hashes every word); call
+ * this after editing the index arrays in place when neither would change. */
+void tcsc_invalidate(const tcsc_t *W);
+
 /* extension: message of the last failure on the calling thread ("" if none) -- the reference's GEMM entry points
  * return void, so this is the only error channel */
 const char *sparse_last_error(void);

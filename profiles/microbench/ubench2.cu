@@ -382,6 +382,58 @@ __global__ void __launch_bounds__(512, 1) k_dispatch(const uint32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// E. does an L1-resident global gather (LDG.128, ld.global.ca) add bandwidth on top of the shared-memory gather?
+// ------------------------------------------------------------------------------------------------------------
+template <int NG, int NS>
+__global__ void __launch_bounds__(512, 1) k_ldgmix(const float *__restrict__ xg, float *out, long long *cyc, int iters, int KC, int KG) {
+    extern __shared__ __align__(16) float xs[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < KC * 128; i += blockDim.x) xs[i] = (float)(i % 97) * 0.01f;
+    __syncthreads();
+    const uint32_t xb = smem_u32(xs) + lane * 16;
+    const float *gb = xg + (size_t)blockIdx.x * KG * 128 + lane * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[j][v] = 0.f;
+    uint32_t k = warp * 7 + 1;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        float4 vg[NG > 0 ? NG : 1];
+        float4 vs[NS > 0 ? NS : 1];
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+            k = k * 5 + 3;
+            const float *a = gb + (size_t)((k >> 4) % (uint32_t)KG) * 128;
+            asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vg[u].x), "=f"(vg[u].y), "=f"(vg[u].z), "=f"(vg[u].w) : "l"(a));
+        }
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+            k = k * 5 + 3;
+            const uint32_t a = xb + ((k >> 4) % (uint32_t)KC) * 512u;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vs[u].x), "=f"(vs[u].y), "=f"(vs[u].z), "=f"(vs[u].w) : "r"(a));
+        }
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+            acc[u & 3][0] += vg[u].x; acc[u & 3][1] += vg[u].y; acc[u & 3][2] += vg[u].z; acc[u & 3][3] += vg[u].w;
+        }
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+            acc[u & 3][0] += vs[u].x; acc[u & 3][1] += vs[u].y; acc[u & 3][2] += vs[u].z; acc[u & 3][3] += vs[u].w;
+        }
+    }
+    long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s += acc[j][v];
+    if (s == 12345.678f) out[2] = s;
+    if (lane == 0) atomicMax((unsigned long long *)&cyc[blockIdx.x], (unsigned long long)(t1 - t0));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------------------
 static int g_nsm = 148;
@@ -442,6 +494,28 @@ int main(int argc, char **argv) {
     CK(cudaMemset(d_out, 0, 1024));
     CK(cudaMalloc(&d_cyc, sizeof(long long) * NSM_MAX));
     const int it = 5000;
+    // E
+    if (argc > 1 && argv[1][0] == 'E') {
+        const int KG = 96;  // 48 KB per SM in L1
+        float *d_xg;
+        CK(cudaMalloc(&d_xg, (size_t)g_nsm * KG * 512));
+        CK(cudaMemset(d_xg, 0, (size_t)g_nsm * KG * 512));
+        auto go = [&](const char *nm, auto kern, int ng, int ns, int KC) {
+            const int smem = KC * 512;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            char full[96];
+            snprintf(full, 96, "%s_kc%d", nm, KC);
+            run(full, (double)it * 4 * (ng + ns) * 16, smem, [&] { kern<<<g_nsm, 512, smem>>>(d_xg, d_out, d_cyc, it, KC, KG); });
+        };
+        for (int KC : {32, 208}) {
+            go("ldgmix_g0_s8", k_ldgmix<0, 8>, 0, 8, KC);
+            go("ldgmix_g8_s0", k_ldgmix<8, 0>, 8, 0, KC);
+            go("ldgmix_g4_s4", k_ldgmix<4, 4>, 4, 4, KC);
+            go("ldgmix_g2_s6", k_ldgmix<2, 6>, 2, 6, KC);
+        }
+        printf("{\"done\": true}\n");
+        return 0;
+    }
 
     // C first: layout checks (cheap, and everything else depends on them)
     {

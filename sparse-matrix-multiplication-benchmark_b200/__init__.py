@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     # ---- reference-named entry points
     L.tcsc_from_dense.argtypes, L.tcsc_from_dense.restype = [vp, i, i], C.POINTER(tcsc_t)
     L.tcsc_free.argtypes, L.tcsc_free.restype = [C.POINTER(tcsc_t)], None
+    L.tcsc_invalidate.argtypes, L.tcsc_invalidate.restype = [C.POINTER(tcsc_t)], None
     for n in ("tcsc_sgemm_basic", "tcsc_sgemm_optimized"):
         getattr(L, n).argtypes, getattr(L, n).restype = [vp, C.POINTER(tcsc_t), vp, vp, i, i, i], None
     for n in ("tcsc_sgemm_prelu_basic", "tcsc_sgemm_prelu_optimized_separate", "tcsc_sgemm_prelu_optimized_onthego"):

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "sparse/bcsr.h"
+#include "tsg_fingerprint.h"
 #include "tsg_host_shim.h"
 #include "tsgemm_b200.h"
 
@@ -14,6 +15,7 @@ typedef struct {
     const float *values; /* key */
     const int *row_start, *col_idx;
     int r, c, br, bc, k;
+    uint64_t fp; /* content hash: free() + rebuild of an equal-shaped matrix returns the same addresses (tsg_fingerprint.h) */
     tsg_bcsr *dev;
 } bmirror;
 
@@ -21,7 +23,39 @@ static bmirror *g_tab = NULL;
 static size_t g_len = 0, g_cap = 0;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 
-static int b_insert(const bcsr_t *W, tsg_bcsr *dev) {
+static uint64_t b_content_fp(const bcsr_t *W) {
+    uint64_t h = 0x6263737200000001ull;
+    const size_t k = W->k > 0 ? (size_t)W->k : 0;
+    h = tsg_fp_words(W->b_row_start, W->b_row_start && W->br >= 0 ? (size_t)W->br + 1 : 0, h);
+    h = tsg_fp_words(W->b_col_idx, W->b_col_idx ? k : 0, h);
+    h = tsg_fp_words(W->b_values, W->b_values ? k * (size_t)W->r * (size_t)W->c : 0, h);
+    return h;
+}
+
+static int b_matches(const bmirror *e, const bcsr_t *W, uint64_t fp) {
+    return e->values == W->b_values && e->row_start == W->b_row_start && e->col_idx == W->b_col_idx && e->r == W->r && e->c == W->c &&
+           e->br == W->br && e->bc == W->bc && e->k == W->k && e->fp == fp;
+}
+
+/* shares an array address with W: the memory it described was free()d by the caller (test/test_bcsr.cpp:48-51 -- the
+ * reference has no bcsr_free, so nothing else tells the library) and handed out again */
+static int b_aliases(const bmirror *e, const bcsr_t *W) {
+    return (W->b_values && e->values == W->b_values) || (W->b_row_start && e->row_start == W->b_row_start) ||
+           (W->b_col_idx && e->col_idx == W->b_col_idx);
+}
+
+#define TSG_MAX_STALE 8
+static size_t b_purge_locked(const bcsr_t *W, tsg_bcsr **stale, size_t ns) {
+    for (size_t i = 0; i < g_len;) {
+        if (b_aliases(&g_tab[i], W)) {
+            if (ns < TSG_MAX_STALE) stale[ns++] = g_tab[i].dev;
+            g_tab[i] = g_tab[--g_len];
+        } else ++i;
+    }
+    return ns;
+}
+
+static int b_insert_locked(const bcsr_t *W, tsg_bcsr *dev, uint64_t fp) {
     if (g_len == g_cap) {
         size_t ncap = g_cap ? 2 * g_cap : 16;
         bmirror *nt = (bmirror *)realloc(g_tab, ncap * sizeof *nt);
@@ -29,30 +63,47 @@ static int b_insert(const bcsr_t *W, tsg_bcsr *dev) {
         g_tab = nt;
         g_cap = ncap;
     }
-    bmirror e = {W->b_values, W->b_row_start, W->b_col_idx, W->r, W->c, W->br, W->bc, W->k, dev};
+    bmirror e = {W->b_values, W->b_row_start, W->b_col_idx, W->r, W->c, W->br, W->bc, W->k, fp, dev};
     g_tab[g_len++] = e;
     return TSG_OK;
 }
 
-static tsg_bcsr *b_mirror_of(const bcsr_t *W) {
-    tsg_bcsr *dev = NULL, *stale = NULL;
+static int b_insert(const bcsr_t *W, tsg_bcsr *dev, uint64_t fp) {
+    tsg_bcsr *stale[TSG_MAX_STALE];
     pthread_mutex_lock(&g_mu);
-    for (size_t i = 0; i < g_len; ++i)
+    size_t ns = b_purge_locked(W, stale, 0);
+    int rc = b_insert_locked(W, dev, fp);
+    pthread_mutex_unlock(&g_mu);
+    for (size_t i = 0; i < ns; ++i) tsg_bcsr_destroy(stale[i]);
+    return rc;
+}
+
+static tsg_bcsr *b_mirror_of(const bcsr_t *W) {
+    const uint64_t fp = b_content_fp(W);
+    tsg_bcsr *dev = NULL;
+    pthread_mutex_lock(&g_mu);
+    for (size_t i = g_len; i-- > 0;) /* newest first */
         if (g_tab[i].values == W->b_values) {
-            const bmirror *e = &g_tab[i];
-            if (e->row_start == W->b_row_start && e->col_idx == W->b_col_idx && e->r == W->r && e->c == W->c && e->br == W->br &&
-                e->bc == W->bc && e->k == W->k)
-                dev = e->dev;
-            else { stale = e->dev; g_tab[i] = g_tab[--g_len]; }
+            if (b_matches(&g_tab[i], W, fp)) dev = g_tab[i].dev;
             break;
         }
-    if (!dev) {
-        if (tsg_bcsr_from_arrays(W->b_row_start, W->b_col_idx, W->b_values, W->r, W->c, W->br, W->bc, W->k, &dev) == TSG_OK) {
-            if (b_insert(W, dev) != TSG_OK) { tsg_bcsr_destroy(dev); dev = NULL; }
-        } else dev = NULL;
+    pthread_mutex_unlock(&g_mu);
+    if (dev) return dev;
+    if (tsg_bcsr_from_arrays(W->b_row_start, W->b_col_idx, W->b_values, W->r, W->c, W->br, W->bc, W->k, &dev) != TSG_OK) return NULL;
+    tsg_bcsr *stale[TSG_MAX_STALE], *winner = NULL;
+    pthread_mutex_lock(&g_mu);
+    for (size_t i = g_len; i-- > 0;)
+        if (g_tab[i].values == W->b_values && b_matches(&g_tab[i], W, fp)) { winner = g_tab[i].dev; break; }
+    size_t ns = 0;
+    if (winner) {
+        stale[ns++] = dev;
+        dev = winner;
+    } else {
+        ns = b_purge_locked(W, stale, 0);
+        if (b_insert_locked(W, dev, fp) != TSG_OK) { stale[ns++] = dev; dev = NULL; }
     }
     pthread_mutex_unlock(&g_mu);
-    if (stale) tsg_bcsr_destroy(stale);
+    for (size_t i = 0; i < ns; ++i) tsg_bcsr_destroy(stale[i]);
     return dev;
 }
 
@@ -60,7 +111,7 @@ void bcsr_release_device(const bcsr_t *W) {
     if (!W) return;
     tsg_bcsr *dev = NULL;
     pthread_mutex_lock(&g_mu);
-    for (size_t i = 0; i < g_len; ++i)
+    for (size_t i = g_len; i-- > 0;)
         if (g_tab[i].values == W->b_values) {
             dev = g_tab[i].dev;
             g_tab[i] = g_tab[--g_len];
@@ -91,11 +142,7 @@ bcsr_t *bcsr_from_dense(dense_t dense, int rows, int cols, int r, int c) { /* bc
     W->b_col_idx = (int *)aligned_alloc(32, round32((size_t)W->k * sizeof(int) + 1));
     int ok = W->b_values && W->b_row_start && W->b_col_idx;
     if (ok) ok = tsg_bcsr_download(dev, W->b_row_start, W->b_col_idx, W->b_values) == TSG_OK;
-    if (ok) {
-        pthread_mutex_lock(&g_mu);
-        ok = b_insert(W, dev) == TSG_OK;
-        pthread_mutex_unlock(&g_mu);
-    }
+    if (ok) ok = b_insert(W, dev, b_content_fp(W)) == TSG_OK; /* purges entries whose (freed) arrays had these addresses */
     if (!ok) {
         free(W->b_values); free(W->b_row_start); free(W->b_col_idx); free(W);
         tsg_bcsr_destroy(dev);
@@ -109,20 +156,7 @@ static void run_bcsr(const float *X, const bcsr_t *W, const float *B, float a, i
     if (M <= 0 || N <= 0) return;
     tsg_bcsr *dev = b_mirror_of(W);
     if (!dev) return;
-    void *dX = NULL, *dB = NULL, *dY = NULL;
-    int ox = 0, ob = 0, oy = 0;
-    if (tsg_shim_stage_in(X, (size_t)M * K * sizeof(float), &dX, &ox) != TSG_OK) return;
-    if (tsg_shim_stage_in(B, (size_t)N * sizeof(float), &dB, &ob) != TSG_OK) { tsg_shim_release(dX, ox); return; }
-    if (tsg_shim_stage_out_begin(Y, (size_t)M * N * sizeof(float), &dY, &oy) != TSG_OK) {
-        tsg_shim_release(dX, ox); tsg_shim_release(dB, ob);
-        return;
-    }
-    if (tsg_bcsr_gemm(dev, (const float *)dX, (const float *)dB, a, use_prelu, (float *)dY, M, N, K, N) == TSG_OK)
-        tsg_shim_stage_out_end(Y, (size_t)M * N * sizeof(float), dY, oy);
-    else
-        tsg_shim_release(dY, oy);
-    tsg_shim_release(dX, ox);
-    tsg_shim_release(dB, ob);
+    tsg_shim_bcsr_gemm_staged(dev, X, B, a, use_prelu, Y, M, N, K);
 }
 
 void bcsr_sgemm_basic(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {

@@ -2,7 +2,7 @@
 //
 // (1) tsg_sparse_gemm_f32: the C-ABI entry behind include/SparseGEMM.h's sparseGEMM<float> / sparseGEMM_PReLU<float>
 //     (reference SparseGEMM.h:104-119,151-168), which take the four raw index arrays instead of a tcsc_t.  The device
-//     mirror is cached per set of array pointers (+ a checksum), because the reference's drivers build the format
+//     mirror is cached per set of array pointers (+ a content hash, tsg_fingerprint.h), because the reference's drivers build the format
 //     once and call the kernel in a timing loop (SparseGEMM.cpp:149-156).
 // (2) C++-mangled forwarders.  The reference's headers carry no extern "C" (sparse/tcsc.h:19-48, sparse/bcsr.h:14-39)
 //     and every documented build compiles the .c files with g++ (README.md:7), so objects compiled against the
@@ -10,56 +10,93 @@
 //     those here lets an unmodified main.cpp / test_bcsr.cpp object link against libtsgemm_b200.so.
 #include <cstdint>
 #include <cstring>
+#include <list>
 #include <mutex>
 #include <vector>
 
+#include "tsg_fingerprint.h"
 #include "tsg_host_shim.h"
 #include "tsgemm_b200.h"
 
 namespace {
 
-struct RawKey {
+// One cached device mirror per set of raw index arrays.  Entries are reference counted: a GEMM holds its entry while
+// it runs, so the LRU eviction and the replacement of a stale entry (same pointers, different contents -- std::vector
+// storage is routinely re-allocated at the same address) never destroy a mirror another thread is still using.
+struct RawEntry {
     const int *csp, *csn, *rip, *rin;
     int N, K;
-    uint64_t sum;
+    uint64_t fp;
     tsg_tcsc *dev;
+    int users;
+    bool dead;  // superseded or evicted while in use: destroyed by the last release
 };
-std::vector<RawKey> g_raw;
+std::list<RawEntry> g_raw;  // oldest first; list nodes keep their address
 std::mutex g_raw_mu;
+constexpr size_t kRawCacheSize = 8;
 
-uint64_t checksum(const int *csp, const int *csn, const int *rip, const int *rin, int N) {
-    uint64_t h = 1469598103934665603ull;
-    auto mix = [&](int v) { h = (h ^ (uint32_t)v) * 1099511628211ull; };
-    for (int i = 0; i <= N; ++i) { mix(csp[i]); mix(csn[i]); }
-    const int np = csp[N], nn = csn[N];
-    for (int i = 0; i < np && i < 64; ++i) mix(rip[i]);
-    for (int i = np > 64 ? np - 64 : 0; i < np; ++i) mix(rip[i]);
-    for (int i = 0; i < nn && i < 64; ++i) mix(rin[i]);
-    for (int i = nn > 64 ? nn - 64 : 0; i < nn; ++i) mix(rin[i]);
+uint64_t raw_fp(const int *csp, const int *csn, const int *rip, const int *rin, int N) {
+    uint64_t h = 0x7261776b00000001ull;
+    h = tsg_fp_words(csp, (size_t)N + 1, h);
+    h = tsg_fp_words(csn, (size_t)N + 1, h);
+    h = tsg_fp_words(rip, csp[N] > 0 ? (size_t)csp[N] : 0, h);
+    h = tsg_fp_words(rin, csn[N] > 0 ? (size_t)csn[N] : 0, h);
     return h;
 }
 
-tsg_tcsc *raw_mirror(const int *csp, const int *csn, const int *rip, const int *rin, int N, int K) {
-    const bool host_arrays = !tsg_shim_is_device(csp);
-    const uint64_t sum = host_arrays ? checksum(csp, csn, rip, rin, N) : 0;
-    std::lock_guard<std::mutex> lk(g_raw_mu);
-    for (size_t i = 0; i < g_raw.size(); ++i) {
-        RawKey &e = g_raw[i];
-        if (e.csp == csp && e.csn == csn && e.rip == rip && e.rin == rin && e.N == N && e.K == K) {
-            if (e.sum == sum) return e.dev;
-            tsg_tcsc_destroy(e.dev);
-            g_raw.erase(g_raw.begin() + i);
-            break;
+void raw_release(RawEntry *e) {
+    tsg_tcsc *doomed = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_raw_mu);
+        if (--e->users == 0 && e->dead) {
+            doomed = e->dev;
+            for (auto it = g_raw.begin(); it != g_raw.end(); ++it)
+                if (&*it == e) { g_raw.erase(it); break; }
         }
     }
+    if (doomed) tsg_tcsc_destroy(doomed);
+}
+
+// returns an entry with users already incremented (release with raw_release), or nullptr
+RawEntry *raw_acquire(const int *csp, const int *csn, const int *rip, const int *rin, int N, int K) {
+    const bool host_arrays = !tsg_shim_is_device(csp);
+    const uint64_t fp = host_arrays ? raw_fp(csp, csn, rip, rin, N) : 0;
+    std::vector<tsg_tcsc *> doomed;
+    RawEntry *hit = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_raw_mu);
+        for (auto it = g_raw.rbegin(); it != g_raw.rend(); ++it) {  // newest first
+            RawEntry &e = *it;
+            if (e.dead || e.csp != csp || e.csn != csn || e.rip != rip || e.rin != rin || e.N != N || e.K != K) continue;
+            if (e.fp == fp) { ++e.users; hit = &e; }
+            else e.dead = true;  // same arrays, new contents
+            break;
+        }
+        if (!hit)
+            for (auto it = g_raw.begin(); it != g_raw.end();) {  // reap what nobody uses any more
+                if (it->dead && it->users == 0) { doomed.push_back(it->dev); it = g_raw.erase(it); }
+                else ++it;
+            }
+    }
+    for (tsg_tcsc *d : doomed) tsg_tcsc_destroy(d);
+    if (hit) return hit;
     tsg_tcsc *dev = nullptr;
     if (tsg_tcsc_from_arrays(csp, csn, rip, rin, K, N, &dev) != TSG_OK) return nullptr;
-    if (g_raw.size() >= 8) {  // small LRU-ish cache
-        tsg_tcsc_destroy(g_raw.front().dev);
-        g_raw.erase(g_raw.begin());
+    doomed.clear();
+    RawEntry *mine = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_raw_mu);
+        size_t live = 0;
+        for (auto &e : g_raw) live += !e.dead;
+        for (auto it = g_raw.begin(); it != g_raw.end() && live >= kRawCacheSize;) {  // evict the oldest idle entries
+            if (!it->dead && it->users == 0) { doomed.push_back(it->dev); it = g_raw.erase(it); --live; }
+            else ++it;
+        }
+        g_raw.push_back(RawEntry{csp, csn, rip, rin, N, K, fp, dev, 1, false});
+        mine = &g_raw.back();
     }
-    g_raw.push_back(RawKey{csp, csn, rip, rin, N, K, sum, dev});
-    return dev;
+    for (tsg_tcsc *d : doomed) tsg_tcsc_destroy(d);
+    return mine;
 }
 
 }  // namespace
@@ -71,21 +108,32 @@ int tsg_sparse_gemm_f32(const float *X, const int *col_start_pos, const int *col
                         const int *row_index_neg, const float *b, float *Y, int M, int N, int K, float a, int use_prelu) {
     tsg_clear_error();
     if (M <= 0 || N <= 0) return TSG_OK;
-    tsg_tcsc *dev = raw_mirror(col_start_pos, col_start_neg, row_index_pos, row_index_neg, N, K);
-    if (!dev) return TSG_ECUDA;
-    if (!tsg_shim_is_device(X) && !tsg_shim_is_device(Y) && (size_t)M * ((size_t)K + (size_t)N) * 4 >= ((size_t)8 << 20))
-        return tsg_shim_tcsc_gemm_hostpipe(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
-    void *dX = nullptr, *dB = nullptr, *dY = nullptr;
-    int ox = 0, ob = 0, oy = 0, rc;
-    if ((rc = tsg_shim_stage_in(X, (size_t)M * K * 4, &dX, &ox))) return rc;
-    if ((rc = tsg_shim_stage_in(b, (size_t)N * 4, &dB, &ob))) { tsg_shim_release(dX, ox); return rc; }
-    if ((rc = tsg_shim_stage_out_begin(Y, (size_t)M * N * 4, &dY, &oy))) { tsg_shim_release(dX, ox); tsg_shim_release(dB, ob); return rc; }
-    rc = tsg_tcsc_gemm(dev, (const float *)dX, (const float *)dB, a, use_prelu, TSG_ORDER_BIAS_LAST, (float *)dY, M, N, K, N);
-    if (rc == TSG_OK) rc = tsg_shim_stage_out_end(Y, (size_t)M * N * 4, dY, oy);
-    else tsg_shim_release(dY, oy);
-    tsg_shim_release(dX, ox);
-    tsg_shim_release(dB, ob);
+    if (!col_start_pos || !col_start_neg) return TSG_EINVAL;
+    RawEntry *ent = raw_acquire(col_start_pos, col_start_neg, row_index_pos, row_index_neg, N, K);
+    if (!ent) return TSG_ECUDA;
+    tsg_tcsc *dev = ent->dev;
+    int rc;
+    if (!tsg_shim_is_device(X) && !tsg_shim_is_device(Y) && (size_t)M * ((size_t)K + (size_t)N) * 4 >= ((size_t)8 << 20)) {
+        rc = tsg_shim_tcsc_gemm_hostpipe(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
+        raw_release(ent);
+        return rc;
+    }
+    rc = tsg_shim_tcsc_gemm_staged(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
+    raw_release(ent);
     return rc;
+}
+
+// drop every cached raw-array mirror that is not in use (extension; e.g. before editing index arrays in place)
+void tsg_sparse_gemm_invalidate(void) {
+    std::vector<tsg_tcsc *> doomed;
+    {
+        std::lock_guard<std::mutex> lk(g_raw_mu);
+        for (auto it = g_raw.begin(); it != g_raw.end();) {
+            if (it->users == 0) { doomed.push_back(it->dev); it = g_raw.erase(it); }
+            else { it->dead = true; ++it; }
+        }
+    }
+    for (tsg_tcsc *d : doomed) tsg_tcsc_destroy(d);
 }
 
 // SparseFormat::SparseFormat (SparseGEMM.h:20-39): int32 matrix, predicates >=1 / <=-1.  Two-call protocol: the first

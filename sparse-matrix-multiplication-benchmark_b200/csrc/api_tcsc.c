@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "sparse/tcsc.h"
+#include "tsg_fingerprint.h"
 #include "tsg_host_shim.h"
 #include "tsgemm_b200.h"
 
@@ -18,21 +19,53 @@
 typedef struct {
     const tcsc_t *host;
     tsg_tcsc *dev;
-    /* fingerprint: a caller may free a tcsc_t and malloc may hand the same address out again */
+    /* fingerprint: a caller may free a tcsc_t and malloc may hand the same addresses out again, or edit the arrays in
+     * place; dimensions, array pointers and a content hash (tsg_fingerprint.h) must all still match */
     int rows, cols, n_pos, n_neg;
     const int *csp, *csn, *rip, *rin;
+    uint64_t fp;
 } mirror_entry;
 
 static mirror_entry *g_tab = NULL;
 static size_t g_tab_len = 0, g_tab_cap = 0;
 static pthread_mutex_t g_tab_mu = PTHREAD_MUTEX_INITIALIZER;
 
-static int entry_matches(const mirror_entry *e, const tcsc_t *W) {
-    return e->host == W && e->rows == W->rows && e->cols == W->cols && e->n_pos == W->n_elem_pos && e->n_neg == W->n_elem_neg &&
-           e->csp == W->col_start_pos && e->csn == W->col_start_neg && e->rip == W->row_index_pos && e->rin == W->row_index_neg;
+static uint64_t content_fp(const tcsc_t *W) {
+    uint64_t h = 0x7463736300000001ull;
+    const size_t nc = W->cols >= 0 ? (size_t)W->cols + 1 : 0;
+    h = tsg_fp_words(W->col_start_pos, W->col_start_pos ? nc : 0, h);
+    h = tsg_fp_words(W->col_start_neg, W->col_start_neg ? nc : 0, h);
+    h = tsg_fp_words(W->row_index_pos, W->n_elem_pos > 0 ? (size_t)W->n_elem_pos : 0, h);
+    h = tsg_fp_words(W->row_index_neg, W->n_elem_neg > 0 ? (size_t)W->n_elem_neg : 0, h);
+    return h;
 }
 
-static int table_insert(const tcsc_t *W, tsg_tcsc *dev) {
+static int entry_matches(const mirror_entry *e, const tcsc_t *W, uint64_t fp) {
+    return e->host == W && e->rows == W->rows && e->cols == W->cols && e->n_pos == W->n_elem_pos && e->n_neg == W->n_elem_neg &&
+           e->csp == W->col_start_pos && e->csn == W->col_start_neg && e->rip == W->row_index_pos && e->rin == W->row_index_neg &&
+           e->fp == fp;
+}
+
+/* an entry that shares the struct address or any array address with W describes memory that has been released and
+ * handed out again (tcsc_free was bypassed, or the caller re-used a struct): it can never be valid once W exists */
+static int entry_aliases(const mirror_entry *e, const tcsc_t *W) {
+    return e->host == W || (W->col_start_pos && e->csp == W->col_start_pos) || (W->col_start_neg && e->csn == W->col_start_neg) ||
+           (W->row_index_pos && e->rip == W->row_index_pos) || (W->row_index_neg && e->rin == W->row_index_neg);
+}
+
+#define TSG_MAX_STALE 8
+/* with g_tab_mu held: drop every entry aliasing W (their mirrors go to stale[] for destruction after unlocking) */
+static size_t purge_aliases_locked(const tcsc_t *W, tsg_tcsc **stale, size_t nstale) {
+    for (size_t i = 0; i < g_tab_len;) {
+        if (entry_aliases(&g_tab[i], W)) {
+            if (nstale < TSG_MAX_STALE) stale[nstale++] = g_tab[i].dev; /* beyond that: leaked rather than freed under the lock */
+            g_tab[i] = g_tab[--g_tab_len];
+        } else ++i;
+    }
+    return nstale;
+}
+
+static int insert_locked(const tcsc_t *W, tsg_tcsc *dev, uint64_t fp) {
     if (g_tab_len == g_tab_cap) {
         size_t ncap = g_tab_cap ? 2 * g_tab_cap : 16;
         mirror_entry *nt = (mirror_entry *)realloc(g_tab, ncap * sizeof *nt);
@@ -41,15 +74,26 @@ static int table_insert(const tcsc_t *W, tsg_tcsc *dev) {
         g_tab_cap = ncap;
     }
     mirror_entry e = {W, dev, W->rows, W->cols, W->n_elem_pos, W->n_elem_neg,
-                      W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg};
+                      W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg, fp};
     g_tab[g_tab_len++] = e;
     return TSG_OK;
+}
+
+/* register W -> dev, replacing whatever the table believed about these addresses */
+static int table_insert(const tcsc_t *W, tsg_tcsc *dev, uint64_t fp) {
+    tsg_tcsc *stale[TSG_MAX_STALE];
+    pthread_mutex_lock(&g_tab_mu);
+    size_t ns = purge_aliases_locked(W, stale, 0);
+    int rc = insert_locked(W, dev, fp);
+    pthread_mutex_unlock(&g_tab_mu);
+    for (size_t i = 0; i < ns; ++i) tsg_tcsc_destroy(stale[i]);
+    return rc;
 }
 
 static tsg_tcsc *table_remove(const tcsc_t *W) {
     tsg_tcsc *dev = NULL;
     pthread_mutex_lock(&g_tab_mu);
-    for (size_t i = 0; i < g_tab_len; ++i)
+    for (size_t i = g_tab_len; i-- > 0;)
         if (g_tab[i].host == W) {
             dev = g_tab[i].dev;
             g_tab[i] = g_tab[--g_tab_len];
@@ -59,24 +103,42 @@ static tsg_tcsc *table_remove(const tcsc_t *W) {
     return dev;
 }
 
-/* mirror of W: cached, or (for a tcsc_t the caller assembled itself / a stale slot) built from W's host arrays */
+/* mirror of W: cached, or (for a tcsc_t the caller assembled itself / a stale slot) built from W's host arrays.  The
+ * hash and the H2D build run outside the table lock. */
 static tsg_tcsc *mirror_of(const tcsc_t *W) {
-    tsg_tcsc *dev = NULL, *stale = NULL;
+    const uint64_t fp = content_fp(W);
+    tsg_tcsc *dev = NULL;
     pthread_mutex_lock(&g_tab_mu);
-    for (size_t i = 0; i < g_tab_len; ++i)
+    for (size_t i = g_tab_len; i-- > 0;) /* newest first */
         if (g_tab[i].host == W) {
-            if (entry_matches(&g_tab[i], W)) dev = g_tab[i].dev;
-            else { stale = g_tab[i].dev; g_tab[i] = g_tab[--g_tab_len]; }
+            if (entry_matches(&g_tab[i], W, fp)) dev = g_tab[i].dev;
             break;
         }
-    if (!dev) {
-        if (tsg_tcsc_from_arrays(W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg, W->rows, W->cols, &dev) == TSG_OK) {
-            if (table_insert(W, dev) != TSG_OK) { tsg_tcsc_destroy(dev); dev = NULL; }
-        } else dev = NULL;
+    pthread_mutex_unlock(&g_tab_mu);
+    if (dev) return dev;
+    if (tsg_tcsc_from_arrays(W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg, W->rows, W->cols, &dev) != TSG_OK)
+        return NULL;
+    tsg_tcsc *stale[TSG_MAX_STALE], *winner = NULL;
+    pthread_mutex_lock(&g_tab_mu);
+    for (size_t i = g_tab_len; i-- > 0;) /* another thread may have mirrored the same W meanwhile */
+        if (g_tab[i].host == W && entry_matches(&g_tab[i], W, fp)) { winner = g_tab[i].dev; break; }
+    size_t ns = 0;
+    if (winner) {
+        stale[ns++] = dev;
+        dev = winner;
+    } else {
+        ns = purge_aliases_locked(W, stale, 0);
+        if (insert_locked(W, dev, fp) != TSG_OK) { stale[ns++] = dev; dev = NULL; }
     }
     pthread_mutex_unlock(&g_tab_mu);
-    if (stale) tsg_tcsc_destroy(stale);
+    for (size_t i = 0; i < ns; ++i) tsg_tcsc_destroy(stale[i]);
     return dev;
+}
+
+/* explicit invalidation for callers that edit a tcsc_t's arrays in place between GEMM calls (extension) */
+void tcsc_invalidate(const tcsc_t *W) {
+    tsg_tcsc *dev = W ? table_remove(W) : NULL;
+    if (dev) tsg_tcsc_destroy(dev);
 }
 
 /* ---- builder (reference sparse/tcsc.c:6-66) ----------------------------------------------------------------- */
@@ -103,11 +165,7 @@ tcsc_t *tcsc_from_dense(dense_t dense, int rows, int cols) {
     W->row_index_neg = (int *)malloc(((size_t)W->n_elem_neg + 1) * sizeof(int));
     int ok = W->col_start_pos && W->col_start_neg && W->row_index_pos && W->row_index_neg;
     if (ok) ok = tsg_tcsc_download(dev, W->col_start_pos, W->col_start_neg, W->row_index_pos, W->row_index_neg) == TSG_OK;
-    if (ok) {
-        pthread_mutex_lock(&g_tab_mu);
-        ok = table_insert(W, dev) == TSG_OK;
-        pthread_mutex_unlock(&g_tab_mu);
-    }
+    if (ok) ok = table_insert(W, dev, content_fp(W)) == TSG_OK; /* also drops entries of freed structs whose addresses malloc re-used */
     if (!ok) { /* tcsc.c:35-43 */
         free(W->col_start_pos); free(W->col_start_neg); free(W->row_index_pos); free(W->row_index_neg);
         free(W);
@@ -140,20 +198,7 @@ static void run_gemm(const float *X, const tcsc_t *W, const float *B, float a, i
         tsg_shim_tcsc_gemm_hostpipe(dev, X, B, a, use_prelu, order, Y, M, N, K);
         return;
     }
-    void *dX = NULL, *dB = NULL, *dY = NULL;
-    int ox = 0, ob = 0, oy = 0;
-    if (tsg_shim_stage_in(X, (size_t)M * K * sizeof(float), &dX, &ox) != TSG_OK) return;
-    if (tsg_shim_stage_in(B, (size_t)N * sizeof(float), &dB, &ob) != TSG_OK) { tsg_shim_release(dX, ox); return; }
-    if (tsg_shim_stage_out_begin(Y, (size_t)M * N * sizeof(float), &dY, &oy) != TSG_OK) {
-        tsg_shim_release(dX, ox); tsg_shim_release(dB, ob);
-        return;
-    }
-    if (tsg_tcsc_gemm(dev, (const float *)dX, (const float *)dB, a, use_prelu, order, (float *)dY, M, N, K, N) == TSG_OK)
-        tsg_shim_stage_out_end(Y, (size_t)M * N * sizeof(float), dY, oy);
-    else
-        tsg_shim_release(dY, oy);
-    tsg_shim_release(dX, ox);
-    tsg_shim_release(dB, ob);
+    tsg_shim_tcsc_gemm_staged(dev, X, B, a, use_prelu, order, Y, M, N, K); /* failure: Y untouched, reason in sparse_last_error() */
 }
 
 void tcsc_sgemm_basic(const dense_t X, const tcsc_t *W, const dense_t B, dense_t Y, int M, int N, int K) {

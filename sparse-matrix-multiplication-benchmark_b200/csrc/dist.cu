@@ -2,14 +2,18 @@
 //
 // W's N columns are split across the ranks (output columns are independent: column n needs col_start_*[n..n+1], its
 // index ranges, b[n] and all of X -- tcsc.c:148-163); X is broadcast, each rank computes its M x (N/P) slab, and the
-// slabs are all-gathered so every rank ends with the full Y.  Two realisations of the exchange:
+// slabs are all-gathered so every rank ends with the full Y.  Realisations of the exchange (tsgemm_b200.h has the
+// caller-side contract of each mode):
 //   mode 0  NCCL:  ncclBroadcast(X); the kernel writes a contiguous slab; ncclAllGather of the slabs; a re-layout
 //                  kernel interleaves them into row-major Y.
-//   mode 1  fused: Y lives in a symmetric cudaMalloc buffer whose CUDA-IPC mappings of all peers are known to the
-//                  kernel; the GEMM epilogue stores each finished row segment into the local Y and straight into
-//                  every peer's Y over NVLink (P2P stores), so the all-gather overlaps the gather-add tile by tile and
-//                  the extra Y round trip of mode 0 disappears.  A 4-byte ncclAllReduce after the kernel is the
+//   mode 1  fused per-lane peer stores: Y lives in a symmetric cudaMalloc buffer whose CUDA-IPC mappings of all peers
+//                  are known to the kernel; the GEMM epilogue stores each finished row segment into the local Y and
+//                  straight into every peer's Y over NVLink.  A 4-byte ncclAllReduce after the kernel is the
 //                  cross-rank completion barrier.
+//   mode 2  copy engines: the kernel bumps progress counters; copy streams wait on them (cuStreamWaitValue32) and push
+//                  finished row blocks with strided 2-D DMA copies while the kernel still runs.
+//   mode 3/4 fused through the TMA engine: every finished 128-row tile is staged in shared memory and written to the
+//                  local Y and every peer's Y with bulk async stores (mode 4: the tile has shared memory of its own).
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded, else the system one), so the
 // library has no link-time NCCL dependency and loads on machines without it.
 #include <dlfcn.h>
@@ -69,18 +73,16 @@ static int load_nccl() {
         if (r__ != 0) return set_error(TSG_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));              \
     } while (0)
 
-// slabs [P][M][wmax] -> Y[M][N] (rank p's columns start at col0(p)); one thread per float4 where possible
-__global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict__ Y, int M, int N, int world, int wmax, int base, int rem) {
+// slabs [P][M][wmax] -> Y[M][N]; rank p owns columns [c0.v[p], c0.v[p+1]) (tsg_dist_partition, passed in so that the
+// kernel never has to invert the dealing rule: ranks with zero columns and ragged last ranks need no special case)
+struct ColStarts { int v[TSG_MAX_PEERS + 1]; };
+__global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict__ Y, int M, int N, int world, int wmax, ColStarts c0) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)M * N) return;
     const int m = (int)(e / N), n = (int)(e % N);
-    // columns are dealt in units of `base` (+1 unit of 32 for the first `rem` ranks): invert tsg_dist_partition
-    int p, c0;
-    const int big = base + 32;
-    if (n < rem * big) { p = n / big; c0 = p * big; }
-    else { p = rem + (base > 0 ? (n - rem * big) / base : 0); c0 = rem * big + (p - rem) * base; }
-    if (p >= world) { p = world - 1; c0 = rem * big + (p - rem) * base; }
-    Y[e] = G[((size_t)p * M + m) * wmax + (n - c0)];
+    int p = 0;
+    while (p + 1 < world && n >= c0.v[p + 1]) ++p;
+    Y[e] = G[((size_t)p * M + m) * wmax + (n - c0.v[p])];
 }
 
 }  // namespace tsg
@@ -249,8 +251,10 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         }
         // every rank must have finished READING its previous Y before a peer overwrites it
         TSG_TRY(tsg_dist_barrier(D));
-        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr));
-        return tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
+        // a failure on this rank must still reach the closing barrier, or the other ranks hang in theirs
+        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr) : TSG_OK;
+        const int rc2 = tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
+        return rc ? rc : rc2;
     }
 
     if (mode == 3 || mode == 4) {
@@ -266,8 +270,9 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         int np = 0;
         for (int p = 1; p < D->world; ++p) peers[np++] = D->y_peer[(D->rank + p) % D->world] + col0;
         TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y
-        if (ncols > 0) TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr, mode == 4 ? 2 : 1));
-        return tsg_dist_barrier(D);
+        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr, mode == 4 ? 2 : 1) : TSG_OK;
+        const int rc2 = tsg_dist_barrier(D);
+        return rc ? rc : rc2;
     }
 
     if (mode == 2) {
@@ -297,60 +302,66 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         }
         TSG_CUDA(cudaMemsetAsync(D->done, 0, sizeof(unsigned int) * 8, st));
         TSG_TRY(tsg_dist_barrier(D));  // peers have finished reading their previous Y
-        TSG_CUDA(cudaEventRecord(D->ev_start, st));
-        Progress prog;
-        const bool trace = getenv("TSG_DIST_TRACE") != nullptr;  // diagnostic: when do the pushes run relative to the kernel?
-        cudaEvent_t tr_k0 = nullptr, tr_k1 = nullptr, tr_g[8] = {nullptr};
-        if (trace) {
-            cudaEventCreate(&tr_k0); cudaEventCreate(&tr_k1);
-            for (int g = 0; g < 8; ++g) cudaEventCreate(&tr_g[g]);
-            cudaEventRecord(tr_k0, st);
-        }
-        if (ncols > 0)
-            TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 0, nullptr, D->done, &prog));
-        if (trace) cudaEventRecord(tr_k1, st);
-        (void)mtiles;
-        // A FEW copy streams (peers dealt round-robin): one stream tops out near 350 GB/s when all ranks push at once,
-        // while one stream per peer makes the blocking stream-wait memory ops alias onto the same hardware queues and
-        // serialise behind one another (both measured at 8 GPUs); TSG_DIST_COPY_STREAMS overrides the default of 2.
-        if (ncols > 0) {
-            int ncs = 2;
-            if (const char *e = getenv("TSG_DIST_COPY_STREAMS")) ncs = atoi(e);
-            if (ncs < 1) ncs = 1;
-            if (ncs > D->world - 1) ncs = D->world - 1;
-            for (int c = 0; c < ncs; ++c) {
-                cudaStream_t cs = D->copy_stream[c];
-                TSG_CUDA(cudaStreamWaitEvent(cs, D->ev_start, 0));
-                for (int g = 0; g < prog.ngroups; ++g) {
-                    int rc = D->wait_value(cs, (unsigned long long)(uintptr_t)(D->done + g), prog.target[g], /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
-                    if (rc != 0) return set_error(TSG_ECUDA, "cuStreamWaitValue32 failed (%d)", rc);
-                    const int r0 = prog.gbound[g] * 128, r1 = (prog.gbound[g + 1] * 128 < M) ? prog.gbound[g + 1] * 128 : M;
-                    for (int p = 1 + c; p < D->world; p += ncs) {
-                        const int q = (D->rank + p) % D->world;  // start with the next rank: the ranks do not all hit one peer at once
-                        TSG_CUDA(cudaMemcpy2DAsync(D->y_peer[q] + (size_t)r0 * N + col0, (size_t)N * 4, Y + (size_t)r0 * N + col0,
-                                                   (size_t)N * 4, (size_t)ncols * 4, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, cs));
+        // a failure between the two barriers must still reach the closing one, or the other ranks hang in theirs
+        auto pushes = [&]() -> int {
+            TSG_CUDA(cudaEventRecord(D->ev_start, st));
+            Progress prog;
+            const bool trace = getenv("TSG_DIST_TRACE") != nullptr;  // diagnostic: when do the pushes run relative to the kernel?
+            cudaEvent_t tr_k0 = nullptr, tr_k1 = nullptr, tr_g[8] = {nullptr};
+            if (trace) {
+                cudaEventCreate(&tr_k0); cudaEventCreate(&tr_k1);
+                for (int g = 0; g < 8; ++g) cudaEventCreate(&tr_g[g]);
+                cudaEventRecord(tr_k0, st);
+            }
+            if (ncols > 0)
+                TSG_TRY(tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 0, nullptr, D->done, &prog));
+            if (trace) cudaEventRecord(tr_k1, st);
+            (void)mtiles;
+            // A FEW copy streams (peers dealt round-robin): one stream tops out near 350 GB/s when all ranks push at once,
+            // while one stream per peer makes the blocking stream-wait memory ops alias onto the same hardware queues and
+            // serialise behind one another (both measured at 8 GPUs); TSG_DIST_COPY_STREAMS overrides the default of 2.
+            if (ncols > 0) {
+                int ncs = 2;
+                if (const char *e = getenv("TSG_DIST_COPY_STREAMS")) ncs = atoi(e);
+                if (ncs < 1) ncs = 1;
+                if (ncs > D->world - 1) ncs = D->world - 1;
+                for (int c = 0; c < ncs; ++c) {
+                    cudaStream_t cs = D->copy_stream[c];
+                    TSG_CUDA(cudaStreamWaitEvent(cs, D->ev_start, 0));
+                    for (int g = 0; g < prog.ngroups; ++g) {
+                        int rc = D->wait_value(cs, (unsigned long long)(uintptr_t)(D->done + g), prog.target[g], /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
+                        if (rc != 0) return set_error(TSG_ECUDA, "cuStreamWaitValue32 failed (%d)", rc);
+                        const int r0 = prog.gbound[g] * 128, r1 = (prog.gbound[g + 1] * 128 < M) ? prog.gbound[g + 1] * 128 : M;
+                        for (int p = 1 + c; p < D->world; p += ncs) {
+                            const int q = (D->rank + p) % D->world;  // start with the next rank: the ranks do not all hit one peer at once
+                            TSG_CUDA(cudaMemcpy2DAsync(D->y_peer[q] + (size_t)r0 * N + col0, (size_t)N * 4, Y + (size_t)r0 * N + col0,
+                                                       (size_t)N * 4, (size_t)ncols * 4, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, cs));
+                        }
+                        if (trace && c == 0) cudaEventRecord(tr_g[g], cs);
                     }
-                    if (trace && c == 0) cudaEventRecord(tr_g[g], cs);
+                    TSG_CUDA(cudaEventRecord(D->ev_copy[c], cs));
+                    TSG_CUDA(cudaStreamWaitEvent(st, D->ev_copy[c], 0));
                 }
-                TSG_CUDA(cudaEventRecord(D->ev_copy[c], cs));
-                TSG_CUDA(cudaStreamWaitEvent(st, D->ev_copy[c], 0));
             }
-        }
-        if (trace) {
-            cudaStreamSynchronize(st);
-            float tk = 0.f;
-            cudaEventElapsedTime(&tk, tr_k0, tr_k1);
-            fprintf(stderr, "[tsg_dist trace rank %d] transpose+kernel %.3f ms; pushes of group done at:", D->rank, tk);
-            for (int g = 0; g < prog.ngroups; ++g) {
-                float tg = 0.f;
-                cudaEventElapsedTime(&tg, tr_k0, tr_g[g]);
-                fprintf(stderr, " g%d(rows %d..%d)=%.3f", g, prog.gbound[g] * 128, prog.gbound[g + 1] * 128, tg);
+            if (trace) {
+                cudaStreamSynchronize(st);
+                float tk = 0.f;
+                cudaEventElapsedTime(&tk, tr_k0, tr_k1);
+                fprintf(stderr, "[tsg_dist trace rank %d] transpose+kernel %.3f ms; pushes of group done at:", D->rank, tk);
+                for (int g = 0; g < prog.ngroups; ++g) {
+                    float tg = 0.f;
+                    cudaEventElapsedTime(&tg, tr_k0, tr_g[g]);
+                    fprintf(stderr, " g%d(rows %d..%d)=%.3f", g, prog.gbound[g] * 128, prog.gbound[g + 1] * 128, tg);
+                }
+                fprintf(stderr, " ms\n");
+                cudaEventDestroy(tr_k0); cudaEventDestroy(tr_k1);
+                for (int g = 0; g < 8; ++g) cudaEventDestroy(tr_g[g]);
             }
-            fprintf(stderr, " ms\n");
-            cudaEventDestroy(tr_k0); cudaEventDestroy(tr_k1);
-            for (int g = 0; g < 8; ++g) cudaEventDestroy(tr_g[g]);
-        }
-        return tsg_dist_barrier(D);  // every rank's pushes have completed => every Y is whole
+            return TSG_OK;
+        };
+        const int rc = pushes();
+        const int rc2 = tsg_dist_barrier(D);  // every rank's pushes have completed => every Y is whole
+        return rc ? rc : rc2;
     }
 
     // mode 0: (2) contiguous slab, (3) ncclAllGather + re-layout
@@ -362,13 +373,21 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
     float *G = nullptr;
     TSG_TRY(dev_alloc_t(&G, (size_t)D->world * M * wmax));
     float *slab = G + (size_t)D->rank * M * wmax;
-    if (ncols > 0) TSG_TRY(tsg_tcsc_gemm(W_local, X, B + col0, a, use_prelu, order, slab, M, ncols, K, wmax));
+    // a failed local GEMM still takes part in the collective (the other ranks are already in it); its error wins
+    const int rc_gemm = (ncols > 0) ? tsg_tcsc_gemm(W_local, X, B + col0, a, use_prelu, order, slab, M, ncols, K, wmax) : TSG_OK;
     TSG_NCCL(g_nccl.AllGather(slab, G, (size_t)M * wmax, ncclFloat32, D->comm, st));
-    const int units = N / 32, base = (units / D->world) * 32, rem = units % D->world;
+    ColStarts c0;
+    for (int p = 0; p <= TSG_MAX_PEERS; ++p) c0.v[p] = N;
+    for (int p = 0; p < D->world; ++p) {
+        int cp, np_;
+        tsg_dist_partition(N, p, D->world, &cp, &np_);
+        c0.v[p] = cp;
+    }
     const long long total = (long long)M * N;
-    k_relayout_slabs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(G, Y, M, N, D->world, wmax, base, rem);
+    k_relayout_slabs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(G, Y, M, N, D->world, wmax, c0);
     TSG_KERNEL_CHECK("k_relayout_slabs");
-    return dev_free(G);
+    const int rc_free = dev_free(G);
+    return rc_gemm ? rc_gemm : rc_free;
 }
 
 }  // extern "C"
@@ -430,11 +449,11 @@ extern "C" int tsg_dbg_peer_store(float *dst, long long ld, int rows, int cols, 
     if (mode == 0) {
         k_peer_store_scattered<<<grid, 512, 0, stream()>>>(dst, ld, rows, cols, iters);
     } else {
-        static bool attr = false;
-        if (!attr) {
+        static std::atomic<unsigned long long> attr_done{0};
+        TSG_TRY(once_per_device(attr_done, [] {
             TSG_CUDA(cudaFuncSetAttribute(k_peer_store_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 256 * 4));
-            attr = true;
-        }
+            return (int)TSG_OK;
+        }));
         k_peer_store_bulk<<<grid, 512, 128 * 256 * 4, stream()>>>(dst, ld, rows, cols, iters);
     }
     TSG_KERNEL_CHECK("k_peer_store");

@@ -168,14 +168,15 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
     if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) {
         const int mtiles = (M + 127) / 128;
         float *XT = nullptr;
-        TSG_TRY(ws_acquire(0, (size_t)mtiles * K * 128 * sizeof(float), reinterpret_cast<void **>(&XT)));
+        WsHold ws(0);
+        TSG_TRY(ws.acquire((size_t)mtiles * K * 128 * sizeof(float), reinterpret_cast<void **>(&XT)));
         TSG_TRY(transpose_x_tiles(X, XT, M, K));
         static const int env_ring = getenv("TSG_BCSR_RING") ? atoi(getenv("TSG_BCSR_RING")) : 1;
         if (g_bcsr_kernel == 2 || (g_bcsr_kernel == 0 && env_ring)) {
             int handled = 0;
             const int rc = bcsr_gemm_ring(W, XT, B, a, use_prelu, Y, M, N, K, ldy, &handled);
             if (rc != TSG_OK || handled) {
-                const int rc2 = ws_release(0);
+                const int rc2 = ws.release();
                 return rc ? rc : rc2;
             }
         }
@@ -193,7 +194,7 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
         }
 #undef TSG_BCSR_LAUNCH
         TSG_KERNEL_CHECK("k_bcsr_gemm");
-        return ws_release(0);
+        return ws.release();
     }
     const long long total = (long long)M * ncov;
     // generic path writes columns [0, ncov): reuse the element kernel with N restricted via ldy addressing

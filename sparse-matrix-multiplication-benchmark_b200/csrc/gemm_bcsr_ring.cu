@@ -113,6 +113,7 @@ static size_t ring_stage_bytes(int kcb, int r, int c, int max_run) {
 }
 
 static int build_bstream(tsg_bcsr *W) {
+    std::lock_guard<std::recursive_mutex> lk(W->mu);
     BStream &bs = W->bs;
     if (bs.built || bs.unsupported) return TSG_OK;
     const int c = W->c, r = W->r;
@@ -358,11 +359,11 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
 
 template <int C>
 static int launch_ring(const BcsrRingParams &p, size_t smem_bytes) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_done{0};  // one per instantiation
+    TSG_TRY(once_per_device(attr_done, [] {
         TSG_CUDA(cudaFuncSetAttribute(k_bcsr_gemm_ring<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM_MAX));
-        attr_set = true;
-    }
+        return (int)TSG_OK;
+    }));
     const int grid = p.units < num_sms() ? p.units : num_sms();
     k_bcsr_gemm_ring<C><<<grid, BR_THREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_bcsr_gemm_ring");

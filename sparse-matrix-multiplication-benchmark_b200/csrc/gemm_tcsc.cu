@@ -529,7 +529,8 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
         return TSG_OK;
     }
     float *XS = nullptr;
-    TSG_TRY(ws_acquire(1, (size_t)groups * K * SK_MT * sizeof(float), reinterpret_cast<void **>(&XS)));
+    WsHold ws(1);
+    TSG_TRY(ws.acquire((size_t)groups * K * SK_MT * sizeof(float), reinterpret_cast<void **>(&XS)));
     k_skinny_pack_x<<<dim3((K + 255) / 256, groups), 256, 0, st>>>(X, XS, M, K);
     TSG_KERNEL_CHECK("k_skinny_pack_x");
     dim3 grid(ctas, groups);
@@ -541,7 +542,7 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
         default: k_tcsc_skinny<8><<<grid, 256, 0, st>>>(XS, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
     }
     TSG_KERNEL_CHECK("k_tcsc_skinny");
-    return ws_release(1);
+    return ws.release();
 }
 
 // ---- host-side planning (pure arithmetic; also exported for the CPU tests: tsg_plan_*) ---------------------------------
@@ -596,12 +597,12 @@ static void plan_progress(const UnitPlan &u, Progress *prog) {
 }
 
 static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_done{0};
+    TSG_TRY(once_per_device(attr_done, [] {
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
+        return (int)TSG_OK;
+    }));
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) {  // bench.py: device time of this kernel alone, measured on the launching stream
@@ -716,7 +717,8 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     GemmParams p;
     p.mtiles = (M + TM - 1) / TM;
     float *XT = nullptr;
-    TSG_TRY(ws_acquire(0, (size_t)p.mtiles * (K > 0 ? K : 1) * TM * sizeof(float), reinterpret_cast<void **>(&XT)));
+    WsHold ws(0);
+    TSG_TRY(ws.acquire((size_t)p.mtiles * (K > 0 ? K : 1) * TM * sizeof(float), reinterpret_cast<void **>(&XT)));
     if (K > 0) TSG_TRY(transpose_x_tiles(X, XT, M, K));
     p.XT = XT; p.cnt = ks.cnt; p.woff = ks.woff; p.body = ks.body; p.B = B; p.Y = Y; p.ldy = ldy;
     p.M = M; p.N = N; p.K = K; p.kc = ks.kc; p.nchunk = (K > 0) ? ks.nchunk : 0; p.ncols_pad = ks.ncols_pad; p.ngroup = ks.ngroup;
@@ -746,7 +748,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         for (int i = 0; i <= prog->ngroups; ++i) p.gbound[i] = prog->gbound[i];
     }
     int rc = launch_tiled(p, smem_bytes, tile_sep);
-    int rc2 = ws_release(0);
+    int rc2 = ws.release();
     return rc ? rc : rc2;
 }
 }  // namespace tsg

@@ -20,6 +20,23 @@ static int copy_in(void *dst_dev, const void *src, size_t bytes) {
     return TSG_OK;
 }
 
+// one warp per column: col_start monotone and inside [0, nnz], rows inside [0, K) and ascending inside the column (the
+// gather stream finds a chunk's entries by binary search, ktformat.cu).  bad: bit 0 pointers, bit 1 row range, bit 2 order
+__global__ void k_validate_tcsc(const int *__restrict__ cs, const int *__restrict__ ri, int N, int K, int nnz, int *__restrict__ bad) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int b = cs[n], e = cs[n + 1];
+    int f = 0;
+    if ((n == 0 && b != 0) || b > e || b < 0 || e > nnz) f |= 1;
+    else
+        for (int t = b + lane; t < e; t += 32) {
+            const int k = ri[t];
+            if (k < 0 || k >= K) f |= 2;
+            if (t > b && ri[t - 1] > k) f |= 4;
+        }
+    if (f) atomicOr(bad, f);
+}
+
 // thread per block-column: count (pass 0) or record (pass 1) the blocks of that column in ascending block-row order
 __global__ void k_bcsr_cols(const int *__restrict__ row_start, const int *__restrict__ col_idx, int br, int bc, int pass,
                             int *__restrict__ cptr, int *__restrict__ crow, int *__restrict__ cblk) {
@@ -42,6 +59,7 @@ __global__ void k_bcsr_cols(const int *__restrict__ row_start, const int *__rest
 }
 
 int bcsr_build_cols(tsg_bcsr *W) {
+    std::lock_guard<std::recursive_mutex> lk(W->mu);
     if (W->col_built) return TSG_OK;
     cudaStream_t st = stream();
     TSG_TRY(dev_alloc_t(&W->cptr, (size_t)W->bc + 2));
@@ -95,6 +113,26 @@ int tsg_tcsc_from_arrays(const int *csp, const int *csn, const int *rip, const i
         return fail(set_error(TSG_EINVAL, "tsg_tcsc_from_arrays: inconsistent column pointers"));
     if ((rc = dev_alloc_t(&W->rip, (size_t)W->n_pos)) || (rc = dev_alloc_t(&W->rin, (size_t)W->n_neg))) return fail(rc);
     if ((rc = copy_in(W->rip, rip, (size_t)W->n_pos * 4)) || (rc = copy_in(W->rin, rin, (size_t)W->n_neg * 4))) return fail(rc);
+    // caller-assembled arrays are checked once, here: the kernels trust them afterwards
+    if (cols > 0) {
+        int *bad = nullptr;
+        if ((rc = dev_alloc_t(&bad, 1))) return fail(rc);
+        int h_bad = 0;
+        cudaMemsetAsync(bad, 0, 4, stream());
+        const unsigned grid = (unsigned)(((size_t)cols * 32 + 255) / 256);
+        k_validate_tcsc<<<grid, 256, 0, stream()>>>(W->csp, W->rip, cols, rows, W->n_pos, bad);
+        k_validate_tcsc<<<grid, 256, 0, stream()>>>(W->csn, W->rin, cols, rows, W->n_neg, bad);
+        const bool ok = cudaGetLastError() == cudaSuccess && cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, stream()) == cudaSuccess &&
+                        cudaStreamSynchronize(stream()) == cudaSuccess;
+        dev_free(bad);
+        if (!ok) return fail(set_error(TSG_ECUDA, "tsg_tcsc_from_arrays: validation failed to run: %s", cudaGetErrorString(cudaGetLastError())));
+        count_launch();
+        count_launch();
+        if (h_bad)
+            return fail(set_error(TSG_EINVAL, "tsg_tcsc_from_arrays: invalid TCSC arrays:%s%s%s", (h_bad & 1) ? " column pointers not monotone from 0" : "",
+                                  (h_bad & 2) ? " row index outside [0, rows)" : "",
+                                  (h_bad & 4) ? " rows not ascending inside a column (tcsc_from_dense emits them ascending, tcsc.c:51-59)" : ""));
+    }
     *out = W;
     return TSG_OK;
 }

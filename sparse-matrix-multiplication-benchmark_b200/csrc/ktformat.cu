@@ -106,6 +106,7 @@ static long long stage_bytes_for(int kc, int tile_words) { return (long long)kc 
 int build_kstream(tsg_tcsc *W, int smem_reserved) {
     // smem_reserved: shared memory the kernel keeps for something else (the separate output tile of dist mode 4); the
     // chunk height is part of the stream's layout, so a different reservation means a different stream
+    std::lock_guard<std::mutex> lk(W->mu);
     if (W->ks.built && W->ks.smem_reserved == smem_reserved) return TSG_OK;
     if (W->ks.built) {
         free_kstream(W->ks);

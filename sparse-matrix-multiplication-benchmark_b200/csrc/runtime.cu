@@ -60,6 +60,8 @@ int ensure_device() {
     return TSG_OK;
 }
 
+int current_device() { return g_dev.checked >= 0 ? g_dev.checked : 0; }
+
 int num_sms() { return g_dev.sms > 0 ? g_dev.sms : 148; }
 
 int dev_alloc(void **out, size_t bytes) {

@@ -1,10 +1,98 @@
 // staging.cu -- host<->device staging for the reference-named entry points (callers hand us host buffers).
 #include <cstdlib>
+#include <cstring>
 
 #include "tsg_host_shim.h"
 #include "tsg_internal.h"
 
 using namespace tsg;
+
+// ---- small and medium host-pointer calls --------------------------------------------------------------------------------
+// The reference's own shapes are tiny (main.cpp:258-264: M=1, K=512, N=2048 ...), so a host-pointer call is dominated by
+// driver round trips, not by bytes.  Calls whose operands fit kArenaBytes go through a per-thread ARENA that lives across
+// calls: X and B are packed into one pinned buffer and reach the device with ONE async copy, the kernel writes Y
+// straight into mapped pinned memory (posted PCIe writes, visible after the stream synchronises), so a call costs one
+// copy, the kernel launches and one synchronisation -- no pool allocation, no second or third copy.  Larger calls use
+// pool allocations and direct copies from/to the caller's buffers.
+namespace {
+
+constexpr size_t kArenaBytes = (size_t)1 << 20;      // X + B staged through the arena up to this size
+constexpr size_t kArenaOutBytes = (size_t)256 << 10;  // Y written through mapped pinned memory up to this size
+
+struct Arena {
+    int device = -1;
+    char *pin = nullptr;      // pinned + mapped host memory: [0, kArenaBytes) inputs, [kArenaBytes, +kArenaOutBytes) output
+    char *pin_dev = nullptr;  // device alias of `pin`
+    char *dev = nullptr;      // device copy of the inputs
+};
+thread_local Arena g_arena;
+
+int arena_get(Arena **out) {
+    int dev = 0;
+    TSG_CUDA(cudaGetDevice(&dev));
+    Arena &a = g_arena;
+    if (a.device != dev) {
+        if (a.pin) cudaFreeHost(a.pin);
+        if (a.dev) cudaFree(a.dev);
+        a = Arena();
+        TSG_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&a.pin), kArenaBytes + kArenaOutBytes, cudaHostAllocMapped));
+        TSG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&a.pin_dev), a.pin, 0));
+        TSG_CUDA(cudaMalloc(reinterpret_cast<void **>(&a.dev), kArenaBytes));
+        a.device = dev;
+    }
+    *out = &a;
+    return TSG_OK;
+}
+
+inline size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+template <typename Gemm>
+int staged_gemm(const float *X, const float *B, float *Y, int M, int N, int K, Gemm gemm) {
+    TSG_TRY(ensure_device());
+    const size_t xb = (size_t)M * K * 4, bb = (size_t)N * 4, yb = (size_t)M * N * 4;
+    const bool x_dev = is_device_pointer(X), b_dev = is_device_pointer(B), y_dev = is_device_pointer(Y);
+    cudaStream_t st = stream();
+    if (x_dev && b_dev && y_dev) return gemm(X, B, Y);  // nothing to stage: asynchronous, like every device-pointer call
+    const size_t in_bytes = (x_dev ? 0 : up256(xb)) + (b_dev ? 0 : up256(bb));
+    if (in_bytes <= kArenaBytes && (y_dev || yb <= kArenaOutBytes)) {
+        Arena *ar = nullptr;
+        TSG_TRY(arena_get(&ar));
+        // the previous call on this thread synchronised before it returned, so the arena is idle
+        size_t off = 0;
+        const float *dX = X, *dB = B;
+        if (!x_dev) { memcpy(ar->pin + off, X, xb); dX = reinterpret_cast<const float *>(ar->dev + off); off += up256(xb); }
+        if (!b_dev) { memcpy(ar->pin + off, B, bb); dB = reinterpret_cast<const float *>(ar->dev + off); off += up256(bb); }
+        if (off) TSG_CUDA(cudaMemcpyAsync(ar->dev, ar->pin, off, cudaMemcpyHostToDevice, st));
+        float *dY = y_dev ? Y : reinterpret_cast<float *>(ar->pin_dev + kArenaBytes);
+        int rc = gemm(dX, dB, dY);
+        // host inputs were staged from the caller's memory by memcpy, so X/B may be reused as soon as we return; the
+        // arena itself must be idle before the next call, and a host Y must be complete
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc) return rc;
+        if (e != cudaSuccess) return set_error(TSG_ECUDA, "staged GEMM failed: %s", cudaGetErrorString(e));
+        if (!y_dev) memcpy(Y, ar->pin + kArenaBytes, yb);
+        return TSG_OK;
+    }
+    void *dX = nullptr, *dB = nullptr, *dY = nullptr;
+    int ox = 0, ob = 0, oy = 0, rc;
+    if ((rc = tsg_shim_stage_in(X, xb, &dX, &ox))) return rc;
+    if ((rc = tsg_shim_stage_in(B, bb, &dB, &ob))) { tsg_shim_release(dX, ox); return rc; }
+    if ((rc = tsg_shim_stage_out_begin(Y, yb, &dY, &oy))) { tsg_shim_release(dX, ox); tsg_shim_release(dB, ob); return rc; }
+    rc = gemm(static_cast<const float *>(dX), static_cast<const float *>(dB), static_cast<float *>(dY));
+    if (rc == TSG_OK) rc = tsg_shim_stage_out_end(Y, yb, dY, oy);  // synchronises when Y is a host buffer
+    else tsg_shim_release(dY, oy);
+    tsg_shim_release(dX, ox);
+    tsg_shim_release(dB, ob);
+    // a host X or B is read by an asynchronous copy (truly asynchronous when it is pinned): with a device Y nothing has
+    // waited for it yet, and the reference's contract is that inputs may be reused once the call returns
+    if (rc == TSG_OK && (ox || ob) && !oy) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return set_error(TSG_ECUDA, "staged GEMM failed: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -42,6 +130,19 @@ int tsg_shim_stage_out_end(void *p, size_t bytes, void *dev, int owned) {
 }
 
 int tsg_shim_release(void *dev, int owned) { return owned ? dev_free(dev) : TSG_OK; }
+
+int tsg_shim_tcsc_gemm_staged(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N,
+                              int K) {
+    return staged_gemm(X, B, Y, M, N, K, [&](const float *dX, const float *dB, float *dY) {
+        return tsg_tcsc_gemm(W, dX, dB, a, use_prelu, order, dY, M, N, K, N);
+    });
+}
+
+int tsg_shim_bcsr_gemm_staged(tsg_bcsr *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K) {
+    return staged_gemm(X, B, Y, M, N, K, [&](const float *dX, const float *dB, float *dY) {
+        return tsg_bcsr_gemm(W, dX, dB, a, use_prelu, dY, M, N, K, N);
+    });
+}
 
 // ---- pipelined host-pointer GEMM ----------------------------------------------------------------------------------------
 // X and Y live in host memory (pinned or pageable).  Rows are independent, so the call is cut into row slabs and the

@@ -16,6 +16,13 @@ int tsg_shim_stage_out_begin(void *p, size_t bytes, void **dev, int *owned);
 /* copy back (if owned), synchronise the stream (if owned) and release */
 int tsg_shim_stage_out_end(void *p, size_t bytes, void *dev, int owned);
 int tsg_shim_release(void *dev, int owned);
+/* Y = [PReLU](X*W + B) for any mix of host and device pointers.  Small host operands go through a per-thread pinned
+ * arena (one H2D copy, Y written through mapped pinned memory, one synchronisation); larger ones through pool
+ * allocations.  Returns after the caller's host buffers are no longer needed (and Y, if a host buffer, is complete);
+ * all-device calls stay asynchronous. */
+int tsg_shim_tcsc_gemm_staged(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N,
+                              int K);
+int tsg_shim_bcsr_gemm_staged(tsg_bcsr *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K);
 /* host-pointer GEMM with the rows of X/Y pipelined over PCIe in slabs (H2D, kernel, D2H overlapped on 3 streams) */
 int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X_host, const float *B_any, float a, int use_prelu, int order,
                                 float *Y_host, int M, int N, int K);

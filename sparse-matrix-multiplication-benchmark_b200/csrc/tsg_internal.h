@@ -2,9 +2,11 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 
 #include "tsgemm_b200.h"
@@ -59,6 +61,35 @@ struct Workspace {
 };
 int ws_acquire(int slot, size_t bytes, void **out);
 int ws_release(int slot);
+// scope guard: the slot is released (event recorded for the next cross-stream user) on every exit path
+struct WsHold {
+    int slot;
+    bool held = false;
+    explicit WsHold(int s) : slot(s) {}
+    WsHold(const WsHold &) = delete;
+    WsHold &operator=(const WsHold &) = delete;
+    int acquire(size_t bytes, void **out) {
+        const int rc = ws_acquire(slot, bytes, out);
+        held = (rc == TSG_OK);
+        return rc;
+    }
+    int release() {
+        if (!held) return TSG_OK;
+        held = false;
+        return ws_release(slot);
+    }
+    ~WsHold() { if (held) ws_release(slot); }
+};
+// function attributes (dynamic shared memory opt-in) are per DEVICE: run `set` once per device and kernel family
+int current_device();
+template <typename F>
+inline int once_per_device(std::atomic<unsigned long long> &done, F set) {
+    const unsigned long long bit = 1ull << (current_device() & 63);
+    if (done.load(std::memory_order_acquire) & bit) return TSG_OK;
+    const int rc = set();  // setting an attribute twice from two threads is harmless
+    if (rc == TSG_OK) done.fetch_or(bit, std::memory_order_release);
+    return rc;
+}
 template <typename T>
 inline int dev_alloc_t(T **out, size_t count) {
     return dev_alloc(reinterpret_cast<void **>(out), count * sizeof(T));
@@ -108,6 +139,7 @@ struct tsg_tcsc {
     int rows = 0, cols = 0, n_pos = 0, n_neg = 0;
     int *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;  // device
     tsg::KStream ks;
+    std::mutex mu;  // the private stream is built lazily inside the first GEMM: concurrent GEMMs on one handle serialise here
 };
 
 struct tsg_bcsr {
@@ -120,6 +152,7 @@ struct tsg_bcsr {
     int *cblk = nullptr;   // [k] index of the block in `values`
     bool col_built = false;
     tsg::BStream bs;
+    std::recursive_mutex mu;  // guards the lazy builds (column index, BStream; the second calls the first)
 };
 
 namespace tsg {
