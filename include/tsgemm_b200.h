@@ -146,6 +146,8 @@ int tsg_dist_peer_ptrs(tsg_dist *D, void *out[8]);
  * mapping) `iters` times; mode 0 = per-lane 64-byte row segments (the fused epilogue's pattern), mode 1 = 1 KB row
  * segments from shared memory with bulk async (TMA) stores */
 int tsg_dbg_peer_store(float *dst, long long ld, int rows, int cols, int iters, int mode);
+/* 1 if the symmetric Y of the last tsg_dist_alloc_y has an NVSwitch multicast mapping (mode 5 usable) */
+int tsg_dist_has_multicast(tsg_dist *D);
 /* stream-ordered cross-rank barrier (4-byte ncclAllReduce on the current stream) */
 int tsg_dist_barrier(tsg_dist *D);
 /* Y(M x N, full, on every rank) = [PReLU](X*W + B).  W_local holds this rank's column slice; B_dev is the full
@@ -159,10 +161,27 @@ int tsg_dist_barrier(tsg_dist *D);
  * mode 3: Y_dev must be the tsg_dist_alloc_y buffer; fused all-gather through the TMA engine: every finished 128-row
  *         tile is staged in shared memory and its row segments are written to the local Y and to every peer's Y with
  *         bulk async stores while the SMs gather the next tile (M >= 32, N and the slab width multiples of 4).
- * mode 4: experimental variant of mode 3: the staged tile gets shared memory of its own (shorter K chunks), so the
- *         stores of one unit drain while the next unit is gathered; same results, not yet measured at N > 1. */
+ * mode 4: variant of mode 3: the staged tile gets shared memory of its own (shorter K chunks), so the stores of one unit
+ *         drain while the next unit is gathered; same results (slower at N = 2: the shorter chunks cost more than the
+ *         overlap returns).
+ * mode 5: NVSwitch multicast: tsg_dist_alloc_y builds the symmetric Y from the virtual-memory API and binds every rank's
+ *         buffer to one multicast object (tsg_dist_has_multicast() tells whether that worked); the kernel stages every
+ *         finished tile in shared memory and writes it ONCE with multimem.st -- the switch replicates it into every
+ *         rank's Y, this rank's included (M >= 32, N and the slab width multiples of 4). */
 int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X_dev, int root, const float *B_dev, float a, int use_prelu,
                   int order, float *Y_dev, int M, int N, int K, int mode);
+
+/* The same with HOST buffers that all ranks share (e.g. one POSIX shared-memory segment mapped by every process; pin it
+ * with tsg_host_register in every process for full PCIe rate).  Every rank moves 1/world of the bytes over ITS OWN PCIe
+ * link: rows [rank*ceil(M/world), ...) of X host->device, ncclAllGather of the row blocks over NVLink, tsg_dist_gemm into
+ * the symmetric Y (tsg_dist_alloc_y must have been called with >= M*N*4 bytes; with world == 1 or mode 0 that buffer is
+ * simply the device copy of Y), the same rows of the full Y device->host.  Synchronous: returns when this rank's rows of
+ * Y_host are complete; Y_host is whole once every rank has returned.  Collective. */
+int tsg_dist_gemm_host(tsg_dist *D, tsg_tcsc *W_local, const float *X_host, const float *B_dev, float a, int use_prelu,
+                       int order, float *Y_host, int M, int N, int K, int mode);
+/* cudaHostRegister / cudaHostUnregister for buffers the caller allocated itself (portable flag) */
+int tsg_host_register(void *p, size_t bytes);
+int tsg_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

@@ -122,7 +122,11 @@ def lib() -> C.CDLL:
     L.tsg_dist_partition.argtypes, L.tsg_dist_partition.restype = [i, i, i, ip, ip], None
     L.tsg_dist_alloc_y.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.tsg_dist_barrier.argtypes = [vp]
+    L.tsg_dist_has_multicast.argtypes = [vp]
     L.tsg_dist_gemm.argtypes = [vp, vp, vp, i, vp, f, i, i, vp, i, i, i, i]
+    L.tsg_dist_gemm_host.argtypes = [vp, vp, vp, vp, f, i, i, vp, i, i, i, i]
+    L.tsg_host_register.argtypes = [vp, C.c_size_t]
+    L.tsg_host_unregister.argtypes = [vp]
     _lib = L
     return L
 
@@ -548,16 +552,36 @@ class Dist:
     def barrier(self):
         _check(lib().tsg_dist_barrier(self.h), "tsg_dist_barrier")
 
+    def has_multicast(self) -> bool:
+        """the symmetric Y of the last alloc_y carries an NVSwitch multicast mapping (mode 5 usable)"""
+        return bool(lib().tsg_dist_has_multicast(self.h))
+
     def gemm(self, W_local: DeviceTcsc, X, B, Y, N, a=0.0, use_prelu=False, order=ORDER_BIAS_LAST, root=0, mode=0):
         M, K = X.shape
         _check(lib().tsg_dist_gemm(self.h, W_local.h, _ptr(X), root, _ptr(B), float(a), int(use_prelu), order, _ptr(Y), M, N, K, mode),
                "tsg_dist_gemm")
         return Y
 
+    def gemm_host(self, W_local: DeviceTcsc, X_host, B, Y_host, N, a=0.0, use_prelu=False, order=ORDER_BIAS_LAST, mode=0):
+        """tsg_dist_gemm_host: X_host / Y_host are numpy arrays over memory shared by all ranks; every rank moves its row
+        block over its own PCIe link.  Returns when this rank's rows of Y_host are complete."""
+        M, K = X_host.shape
+        _check(lib().tsg_dist_gemm_host(self.h, W_local.h, _ptr(X_host, np.float32), _ptr(B), float(a), int(use_prelu), order,
+                                        _ptr(Y_host, np.float32), M, N, K, mode), "tsg_dist_gemm_host")
+        return Y_host
+
     def destroy(self):
         if self.h:
             lib().tsg_dist_destroy(self.h)
             self.h = None
+
+
+def host_register(arr) -> None:
+    _check(lib().tsg_host_register(_ptr(arr), arr.nbytes), "tsg_host_register")
+
+
+def host_unregister(arr) -> None:
+    _check(lib().tsg_host_unregister(_ptr(arr)), "tsg_host_unregister")
 
 
 def _tensor_from_ptr(ptr: int, shape):

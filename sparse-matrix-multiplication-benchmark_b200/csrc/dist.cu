@@ -16,7 +16,10 @@
 //                  local Y and every peer's Y with bulk async stores (mode 4: the tile has shared memory of its own).
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded, else the system one), so the
 // library has no link-time NCCL dependency and loads on machines without it.
+#include <cuda.h>
 #include <dlfcn.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -91,6 +94,62 @@ using namespace tsg;
 
 typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
 
+// ---- driver entry points of the virtual-memory / multicast API, bound at run time (no link-time libcuda dependency) -----
+namespace {
+struct DriverApi {
+    bool tried = false, ok = false;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle *, const CUmulticastObjectProp *) = nullptr;
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+    CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+    CUresult (*MulticastGetGranularity)(size_t *, const CUmulticastObjectProp *, CUmulticastGranularity_flags) = nullptr;
+    CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*DeviceGetAttribute)(int *, CUdevice_attribute, CUdevice) = nullptr;
+};
+DriverApi g_drv;
+
+bool load_driver_api() {
+    if (g_drv.tried) return g_drv.ok;
+    g_drv.tried = true;
+    bool ok = true;
+    auto get = [&](const char *name, void *slot) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); ok = false; return; }
+        *reinterpret_cast<void **>(slot) = fn;
+    };
+    get("cuMemCreate", &g_drv.MemCreate);
+    get("cuMemRelease", &g_drv.MemRelease);
+    get("cuMemAddressReserve", &g_drv.MemAddressReserve);
+    get("cuMemAddressFree", &g_drv.MemAddressFree);
+    get("cuMemMap", &g_drv.MemMap);
+    get("cuMemUnmap", &g_drv.MemUnmap);
+    get("cuMemSetAccess", &g_drv.MemSetAccess);
+    get("cuMemExportToShareableHandle", &g_drv.MemExportToShareableHandle);
+    get("cuMemImportFromShareableHandle", &g_drv.MemImportFromShareableHandle);
+    get("cuMemGetAllocationGranularity", &g_drv.MemGetAllocationGranularity);
+    get("cuMulticastCreate", &g_drv.MulticastCreate);
+    get("cuMulticastAddDevice", &g_drv.MulticastAddDevice);
+    get("cuMulticastBindMem", &g_drv.MulticastBindMem);
+    get("cuMulticastUnbind", &g_drv.MulticastUnbind);
+    get("cuMulticastGetGranularity", &g_drv.MulticastGetGranularity);
+    get("cuDeviceGet", &g_drv.DeviceGet);
+    get("cuDeviceGetAttribute", &g_drv.DeviceGetAttribute);
+    g_drv.ok = ok;
+    return ok;
+}
+}  // namespace
+
 struct tsg_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -104,7 +163,17 @@ struct tsg_dist {
     float *y_local = nullptr;
     size_t y_bytes = 0;
     float *y_peer[TSG_MAX_PEERS] = {nullptr};
+    // symmetric Y from the virtual-memory API with an NVSwitch multicast mapping on top (mode 5): a store to y_mc lands in
+    // the Y of EVERY rank, so a finished tile leaves its GPU once instead of world-1 times
+    bool vmm = false;
+    size_t vmm_size = 0;
+    CUmemGenericAllocationHandle mem = 0, mc = 0, peer_mem[TSG_MAX_PEERS] = {0};
+    CUdeviceptr va_local = 0, va_mc = 0, va_peer[TSG_MAX_PEERS] = {0};
+    float *y_mc = nullptr;
     int *flag = nullptr;
+    // host-buffer entry point: device copy of X assembled from the ranks' row blocks
+    float *x_dev = nullptr;
+    size_t x_bytes = 0;
 };
 
 extern "C" {
@@ -145,17 +214,61 @@ int tsg_dist_create(const unsigned char id128[128], int rank, int world, tsg_dis
         delete D;
         return set_error(TSG_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
     }
-    if (cudaMalloc(&D->flag, 16) != cudaSuccess) {
+    if (cudaMalloc(&D->flag, 32) != cudaSuccess) {
         g_nccl.CommDestroy(D->comm);
         delete D;
         return set_error(TSG_ENOMEM, "cudaMalloc failed");
     }
-    cudaMemset(D->flag, 0, 16);
+    cudaMemset(D->flag, 0, 32);
     *out = D;
     return TSG_OK;
 }
 
+// host-side consensus: true iff `ok` is true on every rank (collective; synchronises the current stream)
+static bool all_ranks_ok(tsg_dist *D, bool ok) {
+    if (D->world == 1) return ok;
+    int h[2] = {ok ? 0 : 1, 0};
+    cudaStream_t st = stream();
+    if (cudaMemcpyAsync(D->flag + 2, &h[0], 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    if (g_nccl.AllReduce(D->flag + 2, D->flag + 3, 1, ncclInt32, ncclSum, D->comm, st) != 0) return false;
+    if (cudaMemcpyAsync(&h[1], D->flag + 3, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+    return h[1] == 0;
+}
+
+static void vmm_release(tsg_dist *D) {
+    if (!g_drv.ok) return;
+    for (int p = 0; p < TSG_MAX_PEERS; ++p) {
+        if (D->va_peer[p]) { g_drv.MemUnmap(D->va_peer[p], D->vmm_size); g_drv.MemAddressFree(D->va_peer[p], D->vmm_size); }
+        if (D->peer_mem[p]) g_drv.MemRelease(D->peer_mem[p]);
+        D->va_peer[p] = 0;
+        D->peer_mem[p] = 0;
+    }
+    if (D->va_mc) { g_drv.MemUnmap(D->va_mc, D->vmm_size); g_drv.MemAddressFree(D->va_mc, D->vmm_size); }
+    if (D->mc && D->mem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        CUdevice cudev;
+        if (g_drv.DeviceGet(&cudev, dev) == CUDA_SUCCESS) g_drv.MulticastUnbind(D->mc, cudev, 0, D->vmm_size);
+    }
+    if (D->va_local) { g_drv.MemUnmap(D->va_local, D->vmm_size); g_drv.MemAddressFree(D->va_local, D->vmm_size); }
+    if (D->mc) g_drv.MemRelease(D->mc);
+    if (D->mem) g_drv.MemRelease(D->mem);
+    D->va_mc = D->va_local = 0;
+    D->mc = D->mem = 0;
+    D->y_mc = nullptr;
+    D->vmm = false;
+    D->vmm_size = 0;
+}
+
 static void dist_unmap(tsg_dist *D) {
+    if (D->vmm) {
+        vmm_release(D);
+        memset(D->y_peer, 0, sizeof D->y_peer);
+        D->y_local = nullptr;
+        D->y_bytes = 0;
+        return;
+    }
     for (int p = 0; p < D->world; ++p)
         if (p != D->rank && D->y_peer[p]) cudaIpcCloseMemHandle(D->y_peer[p]);
     memset(D->y_peer, 0, sizeof D->y_peer);
@@ -164,12 +277,130 @@ static void dist_unmap(tsg_dist *D) {
     D->y_bytes = 0;
 }
 
+#ifndef SYS_pidfd_open
+#define SYS_pidfd_open 434
+#endif
+#ifndef SYS_pidfd_getfd
+#define SYS_pidfd_getfd 438
+#endif
+// duplicate file descriptor `fd` of process `pid` into this process (Linux >= 5.6; same user / same PID namespace)
+static int steal_fd(int pid, int fd) {
+    if (pid == (int)getpid()) return dup(fd);
+    const int pidfd = (int)syscall(SYS_pidfd_open, pid, 0);
+    if (pidfd < 0) return -1;
+    const int got = (int)syscall(SYS_pidfd_getfd, pidfd, fd, 0);
+    close(pidfd);
+    return got;
+}
+
+// Symmetric Y through the virtual-memory API: physical memory per rank (cuMemCreate), mapped locally, bound to ONE
+// multicast object shared by all ranks (created by rank 0, passed around as a POSIX file descriptor that the other
+// processes duplicate with pidfd_getfd), and every peer's memory mapped for unicast access (modes 1-3 keep working).
+// Collective.  Every step ends in a consensus, so either all ranks succeed or all fall back to cudaMalloc + CUDA IPC.
+static bool vmm_alloc_y(tsg_dist *D, size_t bytes) {
+    if (getenv("TSG_DIST_NO_MULTICAST")) return false;  // same on every rank (environment of the launcher)
+    bool ok = load_driver_api();
+    int dev = 0;
+    CUdevice cudev = 0;
+    if (ok) ok = cudaGetDevice(&dev) == cudaSuccess && g_drv.DeviceGet(&cudev, dev) == CUDA_SUCCESS;
+    if (ok) {
+        int mc_ok = 0, fd_ok = 0;
+        g_drv.DeviceGetAttribute(&mc_ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev);
+        g_drv.DeviceGetAttribute(&fd_ok, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, cudev);
+        ok = mc_ok && fd_ok;
+    }
+    if (!all_ranks_ok(D, ok)) return false;
+    cudaStream_t st = stream();
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof ap);
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = dev;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof mp);
+    mp.numDevices = (unsigned)D->world;
+    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t g_alloc = 0, g_mc = 0;
+    mp.size = bytes;
+    ok = g_drv.MemGetAllocationGranularity(&g_alloc, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS &&
+         g_drv.MulticastGetGranularity(&g_mc, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS;
+    size_t gran = g_alloc > g_mc ? g_alloc : g_mc;
+    if (gran == 0) gran = (size_t)2 << 20;
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    mp.size = size;
+    D->vmm_size = size;
+    D->vmm = true;  // from here on dist_unmap releases whatever exists
+    int my_mem_fd = -1, mc_fd = -1;
+    // (1) physical memory + local mapping
+    if (ok) ok = g_drv.MemCreate(&D->mem, size, &ap, 0) == CUDA_SUCCESS;
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (ok) ok = g_drv.MemAddressReserve(&D->va_local, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_local, size, 0, D->mem, 0) == CUDA_SUCCESS &&
+                 g_drv.MemSetAccess(D->va_local, size, &acc, 1) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemExportToShareableHandle(&my_mem_fd, D->mem, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    // (2) the multicast object: rank 0 creates and exports it
+    if (ok && D->rank == 0)
+        ok = g_drv.MulticastCreate(&D->mc, &mp) == CUDA_SUCCESS &&
+             g_drv.MemExportToShareableHandle(&mc_fd, D->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    // (3) everybody learns everybody's (pid, memory fd, multicast fd)
+    struct Card { int pid, mem_fd, mc_fd, ok; };
+    Card mine = {(int)getpid(), my_mem_fd, mc_fd, ok ? 1 : 0}, all[TSG_MAX_PEERS];
+    memset(all, 0, sizeof all);
+    {
+        Card *all_d = nullptr;
+        bool x = cudaMalloc(&all_d, sizeof(Card) * D->world) == cudaSuccess;
+        if (x) x = cudaMemcpyAsync(all_d + D->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (x) x = g_nccl.AllGather(all_d + D->rank, all_d, sizeof mine, /*ncclChar*/ 0, D->comm, st) == 0;  // every rank must take part
+        if (x) x = cudaMemcpyAsync(all, all_d, sizeof(Card) * D->world, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+        if (all_d) cudaFree(all_d);
+        ok = ok && x;
+        for (int p = 0; p < D->world; ++p) ok = ok && all[p].ok;
+    }
+    // (4) import the multicast object, join it, bind my memory, map it
+    if (ok && D->rank != 0) {
+        const int fd = steal_fd(all[0].pid, all[0].mc_fd);
+        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&D->mc, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        if (fd >= 0) close(fd);
+    }
+    if (ok) ok = g_drv.MulticastAddDevice(D->mc, cudev) == CUDA_SUCCESS;
+    ok = all_ranks_ok(D, ok);  // every device has joined before anybody binds
+    if (ok) ok = g_drv.MulticastBindMem(D->mc, 0, D->mem, 0, size, 0) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemAddressReserve(&D->va_mc, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_mc, size, 0, D->mc, 0) == CUDA_SUCCESS &&
+                 g_drv.MemSetAccess(D->va_mc, size, &acc, 1) == CUDA_SUCCESS;
+    // (5) unicast mappings of every peer's memory
+    for (int p = 0; ok && p < D->world; ++p) {
+        if (p == D->rank) continue;
+        const int fd = steal_fd(all[p].pid, all[p].mem_fd);
+        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&D->peer_mem[p], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        if (fd >= 0) close(fd);
+        if (ok) ok = g_drv.MemAddressReserve(&D->va_peer[p], size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_peer[p], size, 0, D->peer_mem[p], 0) == CUDA_SUCCESS &&
+                     g_drv.MemSetAccess(D->va_peer[p], size, &acc, 1) == CUDA_SUCCESS;
+    }
+    ok = all_ranks_ok(D, ok);  // also: nobody closes its descriptors before everybody has duplicated them
+    if (my_mem_fd >= 0) close(my_mem_fd);
+    if (mc_fd >= 0) close(mc_fd);
+    if (!ok) {
+        vmm_release(D);
+        return false;
+    }
+    D->y_local = reinterpret_cast<float *>(D->va_local);
+    D->y_mc = reinterpret_cast<float *>(D->va_mc);
+    D->y_bytes = bytes;
+    for (int p = 0; p < D->world; ++p) D->y_peer[p] = (p == D->rank) ? D->y_local : reinterpret_cast<float *>(D->va_peer[p]);
+    return true;
+}
+
 void tsg_dist_destroy(tsg_dist *D) {
     if (!D) return;
     cudaDeviceSynchronize();
     dist_unmap(D);
     if (D->flag) cudaFree(D->flag);
     if (D->done) cudaFree(D->done);
+    if (D->x_dev) cudaFree(D->x_dev);
     for (int p = 0; p < TSG_MAX_PEERS; ++p) {
         if (D->copy_stream[p]) cudaStreamDestroy(D->copy_stream[p]);
         if (D->ev_copy[p]) cudaEventDestroy(D->ev_copy[p]);
@@ -187,6 +418,10 @@ int tsg_dist_alloc_y(tsg_dist *D, size_t bytes, float **y_local) {
     cudaStream_t st = stream();
     TSG_CUDA(cudaStreamSynchronize(st));
     dist_unmap(D);
+    if (D->world > 1 && vmm_alloc_y(D, bytes)) {  // multicast-capable symmetric buffer (all ranks agree on the outcome)
+        *y_local = D->y_local;
+        return TSG_OK;
+    }
     TSG_CUDA(cudaMalloc(&D->y_local, bytes));
     D->y_bytes = bytes;
     D->y_peer[D->rank] = D->y_local;
@@ -218,6 +453,8 @@ int tsg_dist_peer_ptrs(tsg_dist *D, void *out[TSG_MAX_PEERS]) {
     for (int p = 0; p < TSG_MAX_PEERS; ++p) out[p] = D->y_peer[p];
     return TSG_OK;
 }
+
+int tsg_dist_has_multicast(tsg_dist *D) { return (D && D->y_mc) ? 1 : 0; }
 
 int tsg_dist_barrier(tsg_dist *D) {
     if (!D) return set_error(TSG_EINVAL, "null handle");
@@ -254,6 +491,21 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         // a failure on this rank must still reach the closing barrier, or the other ranks hang in theirs
         const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, np, peers, nullptr, nullptr) : TSG_OK;
         const int rc2 = tsg_dist_barrier(D);  // all peers' stores have landed when every rank's kernel has retired
+        return rc ? rc : rc2;
+    }
+
+    if (mode == 5) {
+        // (2+3 fused, multicast) every finished 128-row tile is staged in shared memory and written ONCE, with multimem.st to
+        // the NVSwitch multicast mapping of the symmetric Y: the switch replicates it into the Y of every rank (this one
+        // included), so a slab leaves its GPU once instead of world-1 times and the epilogue never waits for a drain
+        if (Y != D->y_local) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 5): Y must be the buffer returned by tsg_dist_alloc_y");
+        if (!D->y_mc) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 5): no multicast mapping (tsg_dist_has_multicast() == 0); use mode 3");
+        if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 5): Y buffer too small");
+        if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 5) needs M >= %d", TSG_SKINNY_M);
+        float *peers[1] = {D->y_mc + col0};
+        TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y
+        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 1, peers, nullptr, nullptr, 3) : TSG_OK;
+        const int rc2 = tsg_dist_barrier(D);
         return rc ? rc : rc2;
     }
 
@@ -388,6 +640,49 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
     TSG_KERNEL_CHECK("k_relayout_slabs");
     const int rc_free = dev_free(G);
     return rc_gemm ? rc_gemm : rc_free;
+}
+
+// ---- host-buffer entry point: every rank moves 1/world of the bytes over its own PCIe link ---------------------------------
+int tsg_host_register(void *p, size_t bytes) {
+    TSG_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return TSG_OK;
+}
+int tsg_host_unregister(void *p) {
+    TSG_CUDA(cudaHostUnregister(p));
+    return TSG_OK;
+}
+
+int tsg_dist_gemm_host(tsg_dist *D, tsg_tcsc *W_local, const float *X_host, const float *B_dev, float a, int use_prelu, int order,
+                       float *Y_host, int M, int N, int K, int mode) {
+    if (!D || !W_local || !X_host || !Y_host) return set_error(TSG_EINVAL, "tsg_dist_gemm_host: null argument");
+    if (M <= 0 || N <= 0 || K <= 0) return TSG_OK;
+    TSG_TRY(ensure_device());
+    if (!D->y_local || (size_t)M * N * 4 > D->y_bytes)
+        return set_error(TSG_EINVAL, "tsg_dist_gemm_host: call tsg_dist_alloc_y with at least M*N*4 bytes first");
+    cudaStream_t st = stream();
+    const int rows_per = (M + D->world - 1) / D->world;
+    const int r0 = (D->rank * rows_per < M) ? D->rank * rows_per : M, r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
+    const size_t need = (size_t)rows_per * D->world * K * 4;
+    if (D->x_bytes < need) {
+        TSG_CUDA(cudaStreamSynchronize(st));
+        if (D->x_dev) cudaFree(D->x_dev);
+        D->x_dev = nullptr;
+        D->x_bytes = 0;
+        TSG_CUDA(cudaMalloc(&D->x_dev, need));
+        D->x_bytes = need;
+    }
+    // (1) my row block of X over my PCIe link, then the blocks are all-gathered over NVLink (in place: NCCL's in-place
+    //     all-gather wants sendbuff == recvbuff + rank * count)
+    float *mine = D->x_dev + (size_t)D->rank * rows_per * K;
+    if (r1 > r0) TSG_CUDA(cudaMemcpyAsync(mine, X_host + (size_t)r0 * K, (size_t)(r1 - r0) * K * 4, cudaMemcpyHostToDevice, st));
+    if (D->world > 1) TSG_NCCL(g_nccl.AllGather(mine, D->x_dev, (size_t)rows_per * K, ncclFloat32, D->comm, st));
+    // (2) partitioned GEMM + exchange; every rank ends with the full Y in its symmetric buffer
+    const int rc = tsg_dist_gemm(D, W_local, D->x_dev, -1, B_dev, a, use_prelu, order, D->y_local, M, N, K, mode);
+    // (3) my row block of the full Y back over my PCIe link
+    if (rc == TSG_OK && r1 > r0)
+        TSG_CUDA(cudaMemcpyAsync(Y_host + (size_t)r0 * N, D->y_local + (size_t)r0 * N, (size_t)(r1 - r0) * N * 4, cudaMemcpyDeviceToHost, st));
+    TSG_CUDA(cudaStreamSynchronize(st));
+    return rc;
 }
 
 }  // extern "C"

@@ -313,7 +313,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 }
             }
         }
-        if (p.fused_tma) {
+        if (p.fused_tma == 3) {
+            // tile complete in shared memory -> written ONCE to the NVSwitch multicast mapping of Y (peerY[0], dist.cu mode 5):
+            // the switch replicates every 16-byte store into the Y of every rank, this one included.  A warp covers 512
+            // contiguous bytes of a row per instruction, so the fabric sees full 128-byte lines.
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            const int ncol = min(cw * NWARP, p.N - un.n0);
+            const int rows = min(TM, p.M - un.mt * TM);
+            if (ncol > 0 && rows > 0) {
+                const int nvec = ncol >> 2;
+                float *mc = p.peerY[0] + (size_t)un.mt * TM * p.ldy + un.n0;
+                const float *tile = reinterpret_cast<const float *>(tile_base);
+                for (int i = tid; i < rows * nvec; i += NWARP * 32) {
+                    const int r = i / nvec, c = i - r * nvec;
+                    const float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)r * TILE_PITCH + 4 * c);
+                    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + (size_t)r * p.ldy + 4 * c), "f"(v.x), "f"(v.y),
+                                 "f"(v.z), "f"(v.w)
+                                 : "memory");
+                }
+            }
+            asm volatile("bar.sync 2, 512;" ::: "memory");  // the tile has been read: the producer may refill the ring
+            if (lane == 0) mbar_arrive(epi);
+        } else if (p.fused_tma) {
             // tile complete in shared memory -> one bulk async store (TMA engine) per row and destination
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 2, 512;" ::: "memory");
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             }
         }
     }
-    if (p.fused_tma && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
+    if (p.fused_tma && p.fused_tma != 3 && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
 }
 
 // ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
@@ -728,7 +749,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
     size_t ring_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES);
-    if (fused_tma == 1 && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
+    if ((fused_tma == 1 || fused_tma == 3) && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
     p.tile_off = tile_sep ? (uint32_t)ring_bytes : 0u;
     p.bar_off = (uint32_t)(tile_sep ? ring_bytes + kTileBytes : ring_bytes);
     const size_t smem_bytes = (size_t)p.bar_off + 64;

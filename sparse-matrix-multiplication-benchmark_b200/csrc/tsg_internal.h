@@ -174,7 +174,8 @@ struct Progress {
 };
 // tsg_tcsc_gemm whose epilogue also stores the result into npeer remote copies of Y (fused all-gather, dist.cu);
 // fused_tma: 0 = per-lane stores, 1 = TMA bulk stores from a tile that overlays the stage ring, 2 = TMA bulk stores from
-// a tile of its own (shorter chunks, but the stores of one unit overlap the gathers of the next)
+// a tile of its own (shorter chunks, but the stores of one unit overlap the gathers of the next), 3 = the staged tile is
+// written once with multimem.st to peerY[0] = the NVSwitch multicast mapping of Y (which includes this rank's Y)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                     long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma = 0);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)

@@ -20,9 +20,11 @@ def test_reference_arm_line_has_the_contract_keys():
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     if d["cpu_baseline"]["cores"] > 1:  # all host threads: only the reference's OpenMP form of the path can use them
-        assert "omp" in d["config"]["function"] and "-fopenmp" in d["cpu_baseline"]["build"]
+        assert "omp" in d["details"]["function"] and "-fopenmp" in d["cpu_baseline"]["build"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["value"] > 0 and "workload" in d["config"]
+    # `config` carries workload keys only, identical on both arms (bench.py workload_config): arm-specific facts live in `details`
+    assert set(d["config"]) == {"workload", "M", "K", "N", "sparsity", "nnz", "alpha", "seeds"}
 
 
 def test_reference_arm_single_thread_option():
@@ -30,7 +32,7 @@ def test_reference_arm_single_thread_option():
                           "--ref-threads", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     d = json.loads(out.stdout.strip().splitlines()[-1])
-    assert d["cpu_baseline"]["cores"] == 1 and "tcsc_sgemm_prelu_basic" in d["config"]["function"]
+    assert d["cpu_baseline"]["cores"] == 1 and "tcsc_sgemm_prelu_basic" in d["details"]["function"]
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

@@ -1,0 +1,185 @@
+"""Secondary measurements of bench.py (N = 1): the other BASELINE.json configs and the corners of the sweep
+(configs[2]: K=N=4096, sparsity 50/90/99 %, M = 1/32/256/4096, TCSC and BCSR 1x8), the LLM-layer shape (configs[3]) and the
+conversion kernels, each with its own device time, algorithmic units and roofline fraction.  Shapes follow the reference's
+drivers (main.cpp:258-264, SparseGEMM.cpp:74-80).  Runs outside bench.py's headline timed region; inputs are
+device-resident; small shapes are L2-resident by nature (their whole working set is smaller than the 126 MB L2), which
+`l2` records per entry.
+
+Can be run alone:  python tools/secondary.py [--quick]  -> one JSON object on stdout."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALPHA = 0.2
+L2_BYTES = 126e6
+
+
+def _events(torch, n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _time_calls(torch, fn, reps, warm=2):
+    """mean device ms of fn() over `reps` back-to-back calls (CUDA events on torch's current stream = the library's)"""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = _events(torch, 2)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _bound_entry(name, ms, M, K, N, nnz, peaks, kind="tcsc", stored=None, kernel_ms=None, extra=None):
+    """roofline entry: FP32-add bound (adds = M*nnz) unless the HBM time of the algorithmic bytes is longer (decode shapes)"""
+    hbm_peak, fadd_peak_t, ffma_peak_t = peaks
+    t = (kernel_ms if kernel_ms else ms) * 1e-3
+    bytes_alg = 4.0 * M * K + 4.0 * M * N + 4.0 * N + (4.0 * nnz + 8.0 * (N + 1) if kind == "tcsc" else 4.0 * (stored or 0) + 4.0 * (stored or 0) / 8)
+    e = {"name": name, "call_ms": ms, "M": M, "K": K, "N": N, "nnz": int(nnz)}
+    if kernel_ms:
+        e["kernel_ms"] = kernel_ms
+    t_hbm = bytes_alg / (hbm_peak * 1e9)
+    if kind == "tcsc":
+        units = float(M) * nnz
+        t_cmp = units / (fadd_peak_t * 1e12)
+        cmp_name, cmp_peak, cmp_unit, ach = "fp32_add", fadd_peak_t, "Tadd/s", units / t / 1e12
+    else:
+        units = 2.0 * M * (stored or 0)
+        t_cmp = units / (ffma_peak_t * 1e12)
+        cmp_name, cmp_peak, cmp_unit, ach = "fp32_ffma", ffma_peak_t, "TFLOP/s", units / t / 1e12
+    if t_hbm > t_cmp:
+        e.update({"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / t / 1e9 / hbm_peak,
+                  "algorithmic_bytes": bytes_alg})
+    else:
+        e.update({"bound": cmp_name, "achieved": ach, "peak": cmp_peak, "unit": cmp_unit, "frac": ach / cmp_peak, "algorithmic_units": units})
+    e["l2"] = "working set %.1f MB %s the 126 MB L2" % (bytes_alg / 1e6, "<" if bytes_alg < L2_BYTES else ">")
+    if extra:
+        e.update(extra)
+    return e
+
+
+def run(t, torch, hbm_peak, sm_max_mhz, quick=False):
+    """t: the loaded tsgemm_b200 module.  Returns {"entries": [...], "seconds": wall}"""
+    import time
+    t_start = time.perf_counter()
+    fadd_peak = 148 * 128 * sm_max_mhz * 1e6 / 1e12
+    peaks = (hbm_peak, fadd_peak, 2 * fadd_peak)
+    out = []
+
+    def tcsc_case(name, M, K, N, num, den, reps, seed=42):
+        Wd = t.gen_ternary(K, N, seed, num, den)
+        W = t.DeviceTcsc.from_dense(Wd)
+        del Wd
+        X = t.gen_uniform((M, K), 43)
+        B = t.gen_uniform((N,), 44)
+        Y = torch.empty((M, N), device="cuda")
+        t.profile_enable(True)
+        t.profile_read()
+        ms = _time_calls(torch, lambda: W.gemm(X, B, Y, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST), reps)
+        kms, kn = t.profile_read()
+        t.profile_enable(False)
+        kernel_ms = (kms / kn) if kn else None  # tiled kernel only (includes the warm-up launches: same kernel)
+        out.append(_bound_entry(name, ms, M, K, N, W.nnz, peaks, "tcsc", kernel_ms=kernel_ms,
+                                extra={"sparsity": 1 - num / den, "format": "TCSC", "function": "tcsc_sgemm_prelu_basic order"}))
+        W.destroy()
+
+    def bcsr_case(name, M, K, N, num, den, r, c, reps, seed=42):
+        import ctypes as C
+        Wd = t.gen_ternary(K, N, seed, num, den)
+        h = C.c_void_p()
+        t._check(t.lib().tsg_bcsr_from_dense_f32(t._ptr(Wd), K, N, r, c, C.byref(h)), "tsg_bcsr_from_dense_f32")
+        del Wd
+        dims = [C.c_int() for _ in range(5)]
+        t.lib().tsg_bcsr_dims(h, *[C.byref(d) for d in dims])
+        k = dims[4].value
+        stored = k * r * c
+        X = t.gen_uniform((M, K), 43)
+        B = t.gen_uniform((N,), 44)
+        Y = torch.empty((M, N), device="cuda")
+
+        def call():
+            t._check(t.lib().tsg_bcsr_gemm(h, t._ptr(X), t._ptr(B), ALPHA, 1, t._ptr(Y), M, N, K, N), "tsg_bcsr_gemm")
+        ms = _time_calls(torch, call, reps)
+        out.append(_bound_entry(name, ms, M, K, N, stored, peaks, "bcsr", stored=stored,
+                                extra={"sparsity": 1 - num / den, "format": f"BCSR {r}x{c}", "blocks": k, "function": "bcsr_sgemm_prelu_basic"}))
+        t.lib().tsg_bcsr_destroy(h)
+
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    tcsc_case("cfg1 M64 K512 N512 50% TCSC", 64, 512, 512, 1, 2, 50)
+    # main.cpp:258-264 (the reference driver's shapes, 50 %)
+    tcsc_case("main.cpp M1 K512 N2048 50% TCSC", 1, 512, 2048, 1, 2, 50)
+    tcsc_case("main.cpp M256 K1024 N4096 50% TCSC", 256, 1024, 4096, 1, 2, 20)
+    # configs[2] corners
+    for (num, den, tag) in ((1, 2, "50%"), (1, 10, "90%"), (1, 100, "99%")):
+        for M in (1, 32, 256, 4096):
+            if quick and M == 4096 and tag == "50%":
+                continue
+            reps = 5 if M == 4096 else 20
+            tcsc_case(f"cfg3 M{M} K4096 N4096 {tag} TCSC", M, 4096, 4096, num, den, reps)
+            bcsr_case(f"cfg3 M{M} K4096 N4096 {tag} BCSR1x8", M, 4096, 4096, num, den, 1, 8, 3 if M == 4096 else 10)
+    # the reference's only BCSR GEMM test shape (test/test_bcsr.cpp:13-17)
+    bcsr_case("test_bcsr.cpp M1 K512 N2048 50% BCSR1x8", 1, 512, 2048, 1, 2, 1, 8, 50)
+    # configs[3]
+    if not quick:
+        tcsc_case("cfg4 M8192 K4096 N14336 66% TCSC", 8192, 4096, 14336, 1, 3, 3)
+
+    # conversion kernels: HBM bound, dense matrix read once
+    def convert_case(name, K, N, num, den, reps, fmt="tcsc"):
+        import ctypes as C
+        Wd = t.gen_ternary(K, N, 42, num, den)
+        if fmt == "tcsc":
+            holder = {}
+
+            def call():
+                holder["w"] = t.DeviceTcsc.from_dense(Wd)
+                holder["w"].destroy()
+            ms = _time_calls(torch, call, reps)
+            w = t.DeviceTcsc.from_dense(Wd)
+            nnz = w.nnz
+            w.destroy()
+            bytes_alg = 4.0 * K * N + 4.0 * nnz + 8.0 * (N + 1)
+        else:
+            h = C.c_void_p()
+
+            def call():
+                t._check(t.lib().tsg_bcsr_from_dense_f32(t._ptr(Wd), K, N, 1, 8, C.byref(h)), "tsg_bcsr_from_dense_f32")
+                t.lib().tsg_bcsr_destroy(h)
+            ms = _time_calls(torch, call, reps)
+            t._check(t.lib().tsg_bcsr_from_dense_f32(t._ptr(Wd), K, N, 1, 8, C.byref(h)), "tsg_bcsr_from_dense_f32")
+            dims = [C.c_int() for _ in range(5)]
+            t.lib().tsg_bcsr_dims(h, *[C.byref(d) for d in dims])
+            t.lib().tsg_bcsr_destroy(h)
+            nnz = dims[4].value * 8
+            bytes_alg = 4.0 * K * N + 4.0 * nnz + 4.0 * dims[4].value + 4.0 * (K + 1)
+        out.append({"name": name, "call_ms": ms, "K": K, "N": N, "bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": bytes_alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": bytes_alg,
+                    "note": "whole call: kernels + the host synchronisation that sizes the index arrays + handle allocation"})
+
+    convert_case("convert dense->TCSC 4096x4096 90%", 4096, 4096, 1, 10, 20)
+    convert_case("convert dense->BCSR1x8 4096x4096 90%", 4096, 4096, 1, 10, 10, "bcsr")
+    if not quick:
+        convert_case("convert dense->TCSC 16384x16384 90%", 16384, 16384, 1, 10, 3)
+    torch.cuda.synchronize()
+    return {"entries": out, "seconds": time.perf_counter() - t_start}
+
+
+if __name__ == "__main__":
+    import torch
+
+    import __graft_entry__ as ge
+    torch.cuda.set_device(0)
+    t = ge.load()
+    t.lib()
+    t.use_torch_stream()
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = json.load(open(pk)) if os.path.exists(pk) else {}
+    res = run(t, torch, float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), quick="--quick" in sys.argv)
+    print(json.dumps(res))
