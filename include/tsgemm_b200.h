@@ -36,8 +36,13 @@ enum {
     TSG_ORDER_BIAS_FIRST = 0, /* tcsc_sgemm_basic            tcsc.c:69-98    y=B; +pos...; -neg...            */
     TSG_ORDER_BIAS_LAST = 1,  /* tcsc_sgemm_prelu_basic      tcsc.c:143-165  y=0; +pos...; -neg...; y+=B      */
                               /* sparseGEMM / sparseGEMM_PReLU SparseGEMM.h:104-119,151-168                  */
-    TSG_ORDER_SPLIT = 2       /* tcsc_sgemm_optimized, ..._prelu_optimized_{separate,onthego}
+    TSG_ORDER_SPLIT = 2,      /* tcsc_sgemm_optimized, ..._prelu_optimized_{separate,onthego}
                                  tcsc.c:101-140,179-275      y=(B+fl(sum pos))-fl(sum neg)                    */
+    TSG_ORDER_FAST = 3        /* opt-in, NOT bit-identical to any reference function: one sweep over K, per chunk of rows
+                                 +pos... then -neg..., bias last.  Meets the tolerance contract (max |y-y64| /
+                                 max(|y64|,1) <= 1e-5 or the reference's own error, whichever is larger); X streams
+                                 through shared memory once instead of twice.  tsg_set_fast_order(1) makes the
+                                 reference-named entry points use it.                                                   */
 };
 
 /* below this many rows of X the skinny (decode) kernel runs: lanes over a column's non-zeros + tree reduction */
@@ -81,6 +86,10 @@ int tsg_tcsc_stream_info(tsg_tcsc *W, long long *bytes, int *kc, int *nchunk);
  * column-partitioned path write its slab straight into the full Y). */
 int tsg_tcsc_gemm(tsg_tcsc *W, const float *X_dev, const float *B_dev, float a, int use_prelu, int order,
                   float *Y_dev, int M, int N, int K, long long ldy);
+/* opt-in for the reference-named entry points (tcsc_sgemm_*, sparseGEMM*): 1 = TSG_ORDER_FAST instead of the reference function's
+ * exact order (per thread; default 0; also set by the environment variable TSG_FAST_ORDER=1 at first use) */
+int tsg_set_fast_order(int on);
+int tsg_get_fast_order(void);
 /* force one kernel: 0 auto, 1 tiled shared-memory gather kernel, 2 skinny kernel */
 int tsg_tcsc_set_kernel(int which);
 int tsg_tcsc_get_kernel(void);

@@ -21,7 +21,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSG_LIB_PATH") or os.path.join(HERE, "libtsgemm_b200.so")  # TSG_LIB_PATH: A/B another build of the SAME library
 
-ORDER_BIAS_FIRST, ORDER_BIAS_LAST, ORDER_SPLIT = 0, 1, 2
+ORDER_BIAS_FIRST, ORDER_BIAS_LAST, ORDER_SPLIT, ORDER_FAST = 0, 1, 2, 3
 SKINNY_M = 32
 
 _lib = None
@@ -166,6 +166,11 @@ def use_torch_stream() -> None:
     """Point the library at torch's current CUDA stream (call after torch.cuda.set_device / inside a stream ctx)."""
     import torch
     lib().tsg_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+def set_fast_order(on: bool) -> None:
+    """opt-in: the reference-named entry points use TSG_ORDER_FAST (tolerance contract) instead of the exact order"""
+    lib().tsg_set_fast_order(int(bool(on)))
 
 
 def profile_enable(on: bool) -> None:

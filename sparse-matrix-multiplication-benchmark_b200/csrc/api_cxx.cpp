@@ -112,13 +112,14 @@ int tsg_sparse_gemm_f32(const float *X, const int *col_start_pos, const int *col
     RawEntry *ent = raw_acquire(col_start_pos, col_start_neg, row_index_pos, row_index_neg, N, K);
     if (!ent) return TSG_ECUDA;
     tsg_tcsc *dev = ent->dev;
+    const int order = tsg_get_fast_order() ? TSG_ORDER_FAST : TSG_ORDER_BIAS_LAST;
     int rc;
     if (!tsg_shim_is_device(X) && !tsg_shim_is_device(Y) && (size_t)M * ((size_t)K + (size_t)N) * 4 >= ((size_t)8 << 20)) {
-        rc = tsg_shim_tcsc_gemm_hostpipe(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
+        rc = tsg_shim_tcsc_gemm_hostpipe(dev, X, b, a, use_prelu, order, Y, M, N, K);
         raw_release(ent);
         return rc;
     }
-    rc = tsg_shim_tcsc_gemm_staged(dev, X, b, a, use_prelu, TSG_ORDER_BIAS_LAST, Y, M, N, K);
+    rc = tsg_shim_tcsc_gemm_staged(dev, X, b, a, use_prelu, order, Y, M, N, K);
     raw_release(ent);
     return rc;
 }

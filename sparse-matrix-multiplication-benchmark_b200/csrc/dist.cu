@@ -472,8 +472,32 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
     if (W_local->cols != ncols || W_local->rows != K)
         return set_error(TSG_EINVAL, "tsg_dist_gemm: rank %d owns columns [%d,%d) but W_local is %d x %d", D->rank, col0, col0 + ncols,
                          W_local->rows, W_local->cols);
+    // TSG_DIST_TRACE=1 (diagnostic): per-call device times of the step's phases on this rank, printed to stderr
+    static const bool trace_phases = getenv("TSG_DIST_TRACE") != nullptr;
+    struct PhaseTrace {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        cudaStream_t st;
+        int rank, mode;
+        bool on;
+        PhaseTrace(bool on_, cudaStream_t s, int r, int m) : st(s), rank(r), mode(m), on(on_) {
+            if (on) for (auto &x : e) cudaEventCreate(&x);
+        }
+        void mark(int i) { if (on) cudaEventRecord(e[i], st); }
+        ~PhaseTrace() {
+            if (!on) return;
+            cudaEventRecord(e[2], st);
+            cudaEventSynchronize(e[2]);
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e[0], e[1]);
+            cudaEventElapsedTime(&b, e[1], e[2]);
+            fprintf(stderr, "[tsg_dist phases rank %d mode %d] X broadcast %.3f ms, barrier + GEMM + exchange + barrier %.3f ms\n", rank, mode, a, b);
+            for (auto &x : e) cudaEventDestroy(x);
+        }
+    } trace(trace_phases && D->world > 1, st, D->rank, mode);
+    trace.mark(0);
     // (1) X broadcast
     if (root >= 0 && D->world > 1) TSG_NCCL(g_nccl.Broadcast(X, X, (size_t)M * K, ncclFloat32, root, D->comm, st));
+    trace.mark(1);
     if (D->world == 1) return tsg_tcsc_gemm(W_local, X, B, a, use_prelu, order, Y, M, N, K, N);
 
     if (mode == 1) {

@@ -165,6 +165,12 @@ extern "C" int tsg_bcsr_gemm(tsg_bcsr *W, const float *X, const float *B, float 
         TSG_KERNEL_CHECK("k_bcsr_tail_bias");
     }
     if (bc == 0) return TSG_OK;
+    static const int env_decode = getenv("TSG_DECODE") ? atoi(getenv("TSG_DECODE")) : 1;
+    if (env_decode && M < TSG_SKINNY_M && g_bcsr_kernel == 0) {  // decode shape: lanes over the block list (decode_bcsr.cu), tolerance contract
+        int handled = 0;
+        TSG_TRY(bcsr_decode(W, X, B, a, use_prelu, Y, M, N, K, ldy, &handled));
+        if (handled) return TSG_OK;
+    }
     if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) {
         const int mtiles = (M + 127) / 128;
         float *XT = nullptr;

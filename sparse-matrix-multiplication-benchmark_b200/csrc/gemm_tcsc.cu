@@ -36,6 +36,10 @@ constexpr int REGS_COMPUTE = 112, REGS_PRODUCER = 24;
 constexpr int WOFF_BYTES = 160;  // (256/8 + 1) offsets, rounded up to 16 B
 constexpr int CNT_BYTES = 256;
 constexpr int TILE_PITCH = 260;  // words per row of the staged output tile (fused TMA epilogue)
+// multicast epilogue (fused_tma == 3): the spare warps of the producer warpgroup re-read every finished tile from the local Y
+// (L2) and write it once to the multicast mapping
+constexpr int MC_DRAIN_WARPS = 3;
+constexpr int REGS_PRODUCER_MC = 32;  // the drain loop needs a few more registers than the TMA producer (still inside the re-balancing budget)
 
 struct GemmParams {
     const float *XT;
@@ -108,13 +112,16 @@ __device__ __forceinline__ void gather_chunk(float2 (&acc)[CWMAX][2], uint32_t x
     // word offset of this warp's first column inside the staged body slice
     const int col0 = warp * cw;
     uint32_t off = woff_s[col0 >> 3] - woff_s[0];
-    if (col0 & 7) {  // cw == 4: the warp starts in the middle of an 8-column group
-        const uint32_t prev = *reinterpret_cast<const uint32_t *>(cnt_s + (col0 & ~7));
-        off += 4u * __vsadu4(prev, 0u);
+    if (const int r = col0 & 7) {  // cw < 8: the warp starts inside an 8-column group -> skip the lists of the r columns before it
+        const uint2 prev = *reinterpret_cast<const uint2 *>(cnt_s + (col0 & ~7));
+        const uint32_t lo = (r >= 4) ? prev.x : (prev.x & ((1u << (8 * r)) - 1u));
+        const uint32_t hi = (r > 4) ? (prev.y & ((1u << (8 * (r - 4))) - 1u)) : 0u;
+        off += 4u * (__vsadu4(lo, 0u) + __vsadu4(hi, 0u));
     }
     uint32_t cwd[CWMAX / 4];
 #pragma unroll
-    for (int i = 0; i < CWMAX / 4; ++i) cwd[i] = (4 * i < cw) ? *reinterpret_cast<const uint32_t *>(cnt_s + col0 + 4 * i) : 0u;
+    for (int i = 0; i < CWMAX / 4; ++i) cwd[i] = (4 * i < cw) ? *reinterpret_cast<const uint32_t *>(cnt_s + ((col0 + 4 * i) & ~3)) : 0u;
+    if (cw < 4) cwd[0] = (cwd[0] >> (8 * (col0 & 3))) & ((1u << (8 * cw)) - 1u);  // cw == 2: the warp's two counts sit inside a word
     const uint4 *qp = reinterpret_cast<const uint4 *>(body_s + off);  // every list starts on a 16-byte boundary
     // one quad of look-ahead: the lists of a warp are contiguous in the stream, so the next quad is fetched while the
     // current one is being gathered (reading one quad past the warp's region stays inside the stage buffer)
@@ -161,13 +168,20 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) { return
 
 // TILE_SEP (dist mode 4): the staged output tile has shared memory of its own instead of overlaying the stage ring, so the
 // producer never waits for the bulk stores and a unit's stores drain while the next unit is being gathered.
-template <bool TILE_SEP>
+// MC (dist mode 5): the epilogue hands 32-row slices of the finished tile to three drain warps through two staging buffers of
+// their own; nothing overlays the stage ring and no CTA-wide barrier is left in the unit loop.
+template <bool TILE_SEP, bool MC = false>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t stage_bytes = p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
+    // a stage = X chunk + one stream area (exact orders: the +1 OR the -1 lists of the chunk) or two (TSG_ORDER_FAST: both)
+    const uint32_t area_bytes = p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
+    const bool fast = (p.order == TSG_ORDER_FAST);
+    const uint32_t stage_bytes = p.xstage_bytes + (fast ? 2u : 1u) * area_bytes;
+    const int npass = fast ? 1 : 2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.bar_off);
     uint64_t *empty = full + 2;
     uint64_t *epi = full + 4;  // fused epilogue: consumers -> producer "the output tile has left shared memory"
+    unsigned int *tiles_done = reinterpret_cast<unsigned int *>(full + 5);  // multicast epilogue: compute-warp arrivals, monotonic
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -176,37 +190,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         mbar_init(&empty[0], NWARP);
         mbar_init(&empty[1], NWARP);
         mbar_init(epi, NWARP);
+        *tiles_done = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp >= NWARP) {
         // ===== producer warpgroup: hands its registers to the compute warpgroups; one thread feeds the two-stage ring =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        if (MC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER_MC));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        if (MC && warp > NWARP) {
+            // ===== drain warps (multicast epilogue, dist.cu mode 5): once the 16 compute warps have stored a unit's tile into the
+            // local Y (and fenced), re-read it from L2 and write it ONCE with multimem.st to the NVSwitch multicast mapping of Y
+            // (peerY[0]); the switch replicates every store into the Y of every rank.  A warp moves 512 contiguous bytes of a
+            // row per instruction.  Fabric back-pressure stalls these three warps, never the gather warps, and nothing of the
+            // stage ring is borrowed: the gather loop runs exactly as on one GPU =====
+            const int dwarp = warp - NWARP - 1;
+            uint32_t uidx = 0;
+            for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++uidx) {
+                const Unit un = decode_unit(p, u);
+                const int ncol = min(un.cw * NWARP, p.N - un.n0);
+                const int nvec = ncol > 0 ? (ncol >> 2) : 0;
+                const int m0 = un.mt * TM;
+                const int rows = min(TM, p.M - m0);
+                while (*reinterpret_cast<volatile unsigned int *>(tiles_done) < (uidx + 1u) * NWARP) __nanosleep(256);
+                __threadfence();  // acquire side of the compute warps' fence + arrival
+                const float *src = p.Y + (size_t)m0 * p.ldy + un.n0;
+                float *mc = p.peerY[0] + (size_t)m0 * p.ldy + un.n0;
+                for (int r = dwarp; r < rows; r += MC_DRAIN_WARPS) {
+                    const size_t ro = (size_t)r * p.ldy;
+                    for (int c = lane; c < nvec; c += 32) {
+                        float4 x;
+                        asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(src + ro + 4 * c));
+                        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + ro + 4 * c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+                    }
+                }
+            }
+            return;
+        }
         if (warp == NWARP && lane == 0) {
             uint32_t it = 0, uidx = 0;
             for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++uidx) {
                 const Unit un = decode_unit(p, u);
                 const int tn = un.cw * NWARP;
                 // fused epilogue: the previous unit's output tile overlays the stage ring until its bulk stores have read it
-                if (!TILE_SEP && p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
+                if (!TILE_SEP && !MC && p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
                 const uint32_t woff_copy = (uint32_t)(((tn / 8 + 1) * 4 + 15) & ~15);
-                for (int pass = 0; pass < 2; ++pass) {
+                for (int pass = 0; pass < npass; ++pass) {
                     for (int c = 0; c < p.nchunk; ++c, ++it) {
                         const uint32_t s = it & 1u;
                         mbar_wait(&empty[s], ((it >> 1) & 1u) ^ 1u);
                         uint8_t *st = smem + (size_t)s * stage_bytes;
-                        const int plane = pass * p.nchunk + c;
                         const int rows = min(p.kc, p.K - c * p.kc);
                         const uint32_t xbytes = (uint32_t)rows * (TM * 4);
-                        const size_t gidx = (size_t)plane * p.ngroup + (un.n0 >> 3);
-                        const uint32_t w0 = __ldg(p.woff + gidx), w1 = __ldg(p.woff + gidx + tn / 8);
-                        const uint32_t bbytes = (w1 - w0) * 4u;
-                        mbar_arrive_expect_tx(&full[s], xbytes + bbytes + tn + woff_copy);
+                        // stream slices of this chunk: plane `pass*nchunk + c` (exact orders), or the +1 and the -1 plane (fast order)
+                        size_t gidx[2];
+                        uint32_t w0[2], bbytes[2], total = xbytes;
+                        const int nareas = fast ? 2 : 1;
+                        for (int q = 0; q < nareas; ++q) {
+                            const int plane = (fast ? q : pass) * p.nchunk + c;
+                            gidx[q] = (size_t)plane * p.ngroup + (un.n0 >> 3);
+                            w0[q] = __ldg(p.woff + gidx[q]);
+                            bbytes[q] = (__ldg(p.woff + gidx[q] + tn / 8) - w0[q]) * 4u;
+                            total += bbytes[q] + tn + woff_copy;
+                        }
+                        mbar_arrive_expect_tx(&full[s], total);
                         bulk_g2s(st, p.XT + ((size_t)un.mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
-                        if (bbytes) bulk_g2s(st + p.xstage_bytes, p.body + w0, bbytes, &full[s]);
-                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + un.n0, tn, &full[s]);
-                        bulk_g2s(st + p.xstage_bytes + p.body_stage_bytes + CNT_BYTES, p.woff + gidx, woff_copy, &full[s]);
+                        for (int q = 0; q < nareas; ++q) {
+                            const int plane = (fast ? q : pass) * p.nchunk + c;
+                            uint8_t *area = st + p.xstage_bytes + (size_t)q * area_bytes;
+                            if (bbytes[q]) bulk_g2s(area, p.body + w0[q], bbytes[q], &full[s]);
+                            bulk_g2s(area + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + un.n0, tn, &full[s]);
+                            bulk_g2s(area + p.body_stage_bytes + CNT_BYTES, p.woff + gidx[q], woff_copy, &full[s]);
+                        }
                     }
                 }
             }
@@ -232,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             acc[j][0] = make_float2(init, init);
             acc[j][1] = acc[j][0];
         }
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < npass; ++pass) {
             if (pass == 1 && p.order == TSG_ORDER_SPLIT) {
                 // tcsc.c:125,138: Y = B + acc_pos is rounded and parked in Y, acc_neg starts from 0
 #pragma unroll
@@ -259,6 +315,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const uint32_t *woff_s = reinterpret_cast<const uint32_t *>(cnt_s + CNT_BYTES);
                 if (neg) gather_chunk<true>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
                 else gather_chunk<false>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
+                if (fast) {  // the chunk's -1 entries while the chunk is still resident: X streams through shared memory once
+                    const uint8_t *area = st + p.xstage_bytes + area_bytes;
+                    gather_chunk<true>(acc, xbase, area + p.body_stage_bytes, reinterpret_cast<const uint32_t *>(area + p.body_stage_bytes + CNT_BYTES),
+                                       reinterpret_cast<const uint32_t *>(area), warp, cw);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
@@ -285,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const float av = (v & 1) ? pr.y : pr.x;
                 float y = av;
                 if (j < cw) {
-                    if (p.order == TSG_ORDER_BIAS_LAST) y = av + bias_of(j);                                   // tcsc.c:161
+                    if (p.order == TSG_ORDER_BIAS_LAST || p.order == TSG_ORDER_FAST) y = av + bias_of(j);      // tcsc.c:161
                     else if (p.order == TSG_ORDER_SPLIT) y = ((nbase + j < p.N && m < p.M) ? yrow[j] : 0.f) - av;          // tcsc.c:138
                     if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;                                              // tcsc.c:162
                 }
@@ -313,28 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 }
             }
         }
-        if (p.fused_tma == 3) {
-            // tile complete in shared memory -> written ONCE to the NVSwitch multicast mapping of Y (peerY[0], dist.cu mode 5):
-            // the switch replicates every 16-byte store into the Y of every rank, this one included.  A warp covers 512
-            // contiguous bytes of a row per instruction, so the fabric sees full 128-byte lines.
-            asm volatile("bar.sync 2, 512;" ::: "memory");
-            const int ncol = min(cw * NWARP, p.N - un.n0);
-            const int rows = min(TM, p.M - un.mt * TM);
-            if (ncol > 0 && rows > 0) {
-                const int nvec = ncol >> 2;
-                float *mc = p.peerY[0] + (size_t)un.mt * TM * p.ldy + un.n0;
-                const float *tile = reinterpret_cast<const float *>(tile_base);
-                for (int i = tid; i < rows * nvec; i += NWARP * 32) {
-                    const int r = i / nvec, c = i - r * nvec;
-                    const float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)r * TILE_PITCH + 4 * c);
-                    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + (size_t)r * p.ldy + 4 * c), "f"(v.x), "f"(v.y),
-                                 "f"(v.z), "f"(v.w)
-                                 : "memory");
-                }
-            }
-            asm volatile("bar.sync 2, 512;" ::: "memory");  // the tile has been read: the producer may refill the ring
-            if (lane == 0) mbar_arrive(epi);
-        } else if (p.fused_tma) {
+        if (p.fused_tma) {
             // tile complete in shared memory -> one bulk async store (TMA engine) per row and destination
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 2, 512;" ::: "memory");
@@ -357,6 +397,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 if (lane == 0) mbar_arrive(epi);
             }
         }
+        if constexpr (MC) {  // this warp's share of the tile is in the local Y: let the drain warps send it
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(tiles_done, 1u);
+        }
         if (p.done) {  // publish: this warp's share of unit (mt, n0) is in memory
             __threadfence_system();
             __syncwarp();
@@ -367,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             }
         }
     }
-    if (p.fused_tma && p.fused_tma != 3 && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
+    if (!MC && p.fused_tma && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
 }
 
 // ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
@@ -537,6 +582,12 @@ static thread_local int g_profile = 0;
 static thread_local std::vector<cudaEvent_t> g_prof_events;
 
 static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy) {
+    static const int env_decode = getenv("TSG_DECODE") ? atoi(getenv("TSG_DECODE")) : 1;  // 0: the first skinny kernels (A/B runs)
+    if (env_decode) {  // X rows in shared memory (decode_tcsc.cu); not handled when a row of X does not fit
+        int handled = 0;
+        TSG_TRY(tcsc_decode(W, X, B, a, use_prelu, Y, M, N, K, ldy, &handled));
+        if (handled) return TSG_OK;
+    }
     cudaStream_t st = stream();
     const int groups = (M + SK_MT - 1) / SK_MT;
     const int warps_per_cta = 8;
@@ -579,6 +630,28 @@ static UnitPlan plan_units(int M, int N, int sms) {
     u.ntiles = (N + CWMAX * NWARP - 1) / (CWMAX * NWARP);
     const int U = u.mtiles * u.ntiles;
     u.units_full = (U / sms) * sms;
+    static const int force_sub = getenv("TSG_FORCE_SUB") ? atoi(getenv("TSG_FORCE_SUB")) : 0;  // experiment: every tile cut into 2 or 4 units
+    if (force_sub == 2 || force_sub == 4) {
+        u.units_full = 0;
+        u.sub = force_sub;
+        u.units_total = U * force_sub;
+        return u;
+    }
+    if (U < sms) {
+        // fewer tiles than SMs (mid-size M, narrow W): cut EVERY tile into `sub` units of 256/sub columns.  A narrower unit
+        // still streams the whole X tile, so its time does not fall below the fill-bound floor (about 1/8 of a full unit)
+        int best_sub = 1;
+        double best = 1e30;
+        for (int sub = 1; sub <= 8; sub *= 2) {
+            const double unit = 1.0 / sub + 0.06;
+            const double cost = (double)((U * sub + sms - 1) / sms) * (unit > 0.125 ? unit : 0.125);
+            if (cost < best - 1e-9) { best = cost; best_sub = sub; }
+        }
+        u.units_full = 0;
+        u.sub = best_sub;
+        u.units_total = U * best_sub;
+        return u;
+    }
     const int R = U - u.units_full;
     u.sub = 1;
     if (R > 0) {
@@ -617,11 +690,12 @@ static void plan_progress(const UnitPlan &u, Progress *prog) {
     }
 }
 
-static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep) {
+static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, bool mc = false) {
     static std::atomic<unsigned long long> attr_done{0};
     TSG_TRY(once_per_device(attr_done, [] {
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         return (int)TSG_OK;
     }));
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
@@ -631,7 +705,8 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep) {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream());
     }
-    if (tile_sep) k_tcsc_gemm<true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    if (mc) k_tcsc_gemm<false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    else if (tile_sep) k_tcsc_gemm<true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else k_tcsc_gemm<false><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_tcsc_gemm");
     if (g_profile) {
@@ -651,6 +726,19 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
 }
 
 extern "C" {
+
+static thread_local int g_fast_order = -1;  // -1: not decided yet (environment TSG_FAST_ORDER)
+int tsg_set_fast_order(int on) {
+    g_fast_order = on ? 1 : 0;
+    return TSG_OK;
+}
+int tsg_get_fast_order(void) {
+    if (g_fast_order < 0) {
+        const char *e = getenv("TSG_FAST_ORDER");
+        g_fast_order = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return g_fast_order;
+}
 
 int tsg_tcsc_set_kernel(int which) {
     g_force_kernel = which;
@@ -719,7 +807,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     if (npeer < 0 || npeer > TSG_MAX_PEERS) return set_error(TSG_EINVAL, "too many peers");
     if (!W || !X || !B || !Y) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: null argument");
     if (N != W->cols || K != W->rows) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: W is %d x %d but K=%d, N=%d", W->rows, W->cols, K, N);
-    if (order < 0 || order > 2) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
+    if (order < 0 || order > 3) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: bad order %d", order);
     if (ldy < N) return set_error(TSG_EINVAL, "tsg_tcsc_gemm: ldy < N");
     if (!fused_tma && npeer == 0 && !done) {  // TSG_FUSED_EPILOGUE=1|2: route the single-GPU store through the TMA epilogue too (2 = separate tile)
         static const int env_fused = getenv("TSG_FUSED_EPILOGUE") ? atoi(getenv("TSG_FUSED_EPILOGUE")) : 0;
@@ -731,10 +819,12 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     const bool skinny = npeer == 0 && !done && !fused_tma && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
     if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
 
-    const bool tile_sep = (fused_tma == 2);
+    const bool tile_sep = (fused_tma == 2), mc = (fused_tma == 3);
     constexpr int kTileBytes = TM * TILE_PITCH * 4;
-    TSG_TRY(build_kstream(W, tile_sep ? kTileBytes : 0));
-    const KStream &ks = W->ks;
+    const int sep_bytes = tile_sep ? kTileBytes : 0;  // shared memory behind the ring that is not part of it
+    const bool fast = (order == TSG_ORDER_FAST);
+    TSG_TRY(build_kstream(W, sep_bytes, fast ? 2 : 1));
+    const KStream &ks = fast ? W->ks_fast : W->ks;
     GemmParams p;
     p.mtiles = (M + TM - 1) / TM;
     float *XT = nullptr;
@@ -744,22 +834,22 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     p.XT = XT; p.cnt = ks.cnt; p.woff = ks.woff; p.body = ks.body; p.B = B; p.Y = Y; p.ldy = ldy;
     p.M = M; p.N = N; p.K = K; p.kc = ks.kc; p.nchunk = (K > 0) ? ks.nchunk : 0; p.ncols_pad = ks.ncols_pad; p.ngroup = ks.ngroup;
     p.a = a; p.use_prelu = use_prelu; p.order = order;
-    p.npeer = npeer;
+    p.npeer = (fused_tma == 3) ? 0 : npeer;  // multicast: peerY[0] is the multicast mapping, used by the drain warps only
     for (int q = 0; q < TSG_MAX_PEERS; ++q) p.peerY[q] = (q < npeer) ? peerY[q] : nullptr;
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
-    size_t ring_bytes = 2 * (size_t)(p.xstage_bytes + p.body_stage_bytes + CNT_BYTES + WOFF_BYTES);
-    if ((fused_tma == 1 || fused_tma == 3) && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
-    p.tile_off = tile_sep ? (uint32_t)ring_bytes : 0u;
-    p.bar_off = (uint32_t)(tile_sep ? ring_bytes + kTileBytes : ring_bytes);
-    const size_t smem_bytes = (size_t)p.bar_off + 64;
+    size_t ring_bytes = 2 * ((size_t)p.xstage_bytes + (fast ? 2 : 1) * (size_t)(p.body_stage_bytes + CNT_BYTES + WOFF_BYTES));
+    if (fused_tma == 1 && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
+    p.tile_off = sep_bytes ? (uint32_t)ring_bytes : 0u;
+    p.bar_off = (uint32_t)(ring_bytes + sep_bytes);
+    const size_t smem_bytes = (size_t)p.bar_off + 96;
     if (smem_bytes > 232448) return set_error(TSG_EUNSUPPORTED, "tsg_tcsc_gemm: the gather stream of this matrix leaves no room for a separate output tile");
     const UnitPlan up = plan_units(M, N, num_sms());
     p.ntiles = up.ntiles;
     p.units_full = up.units_full;
     p.sub = up.sub;
     p.units_total = up.units_total;
-    p.fused_tma = fused_tma;
+    p.fused_tma = mc ? 0 : fused_tma;  // the multicast variant stores its tile like the single-GPU kernel; its drain warps do the rest
     p.done = done;
     p.ngroups = 0;
     for (int g = 0; g < 9; ++g) p.gbound[g] = 0;
@@ -768,7 +858,7 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         p.ngroups = prog->ngroups;
         for (int i = 0; i <= prog->ngroups; ++i) p.gbound[i] = prog->gbound[i];
     }
-    int rc = launch_tiled(p, smem_bytes, tile_sep);
+    int rc = launch_tiled(p, smem_bytes, tile_sep, mc);
     int rc2 = ws.release();
     return rc ? rc : rc2;
 }

@@ -141,6 +141,7 @@ void tsg_tcsc_destroy(tsg_tcsc *W) {
     if (!W) return;
     dev_free(W->csp); dev_free(W->csn); dev_free(W->rip); dev_free(W->rin);
     dev_free(W->ks.cnt); dev_free(W->ks.woff); dev_free(W->ks.body);
+    dev_free(W->ks_fast.cnt); dev_free(W->ks_fast.woff); dev_free(W->ks_fast.body);
     delete W;
 }
 
@@ -203,7 +204,7 @@ int tsg_bcsr_from_arrays(const int *row_start, const int *col_idx, const float *
 void tsg_bcsr_destroy(tsg_bcsr *W) {
     if (!W) return;
     dev_free(W->row_start); dev_free(W->col_idx); dev_free(W->values);
-    dev_free(W->cptr); dev_free(W->crow); dev_free(W->cblk);
+    dev_free(W->cptr); dev_free(W->crow); dev_free(W->cblk); dev_free(W->cval);
     dev_free(W->bs.cnt); dev_free(W->bs.wstart); dev_free(W->bs.eoff); dev_free(W->bs.hdr); dev_free(W->bs.val);
     delete W;
 }

@@ -138,7 +138,8 @@ struct BStream {
 struct tsg_tcsc {
     int rows = 0, cols = 0, n_pos = 0, n_neg = 0;
     int *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;  // device
-    tsg::KStream ks;
+    tsg::KStream ks;       // exact orders: one stream slice per pipeline stage
+    tsg::KStream ks_fast;  // TSG_ORDER_FAST: the +1 and the -1 slice of a chunk share a stage (shorter chunks)
     std::mutex mu;  // the private stream is built lazily inside the first GEMM: concurrent GEMMs on one handle serialise here
 };
 
@@ -151,6 +152,7 @@ struct tsg_bcsr {
     int *crow = nullptr;   // [k] block-row of each block in column-major order
     int *cblk = nullptr;   // [k] index of the block in `values`
     bool col_built = false;
+    float *cval = nullptr;  // [k][r*c] block values in column-major block order (decode kernel, decode_bcsr.cu); built lazily
     tsg::BStream bs;
     std::recursive_mutex mu;  // guards the lazy builds (column index, BStream; the second calls the first)
 };
@@ -160,7 +162,7 @@ namespace tsg {
 int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t *total_dev);
 // classify a pointer: 1 device (or managed), 0 host
 int is_device_pointer(const void *p);
-int build_kstream(tsg_tcsc *W, int smem_reserved = 0);
+int build_kstream(tsg_tcsc *W, int smem_reserved = 0, int areas = 1);
 int bcsr_build_cols(tsg_bcsr *W);
 // ring kernel for BCSR (gemm_bcsr_ring.cu): *handled = 0 when the matrix does not fit its limits (caller falls back
 // to the plain kernel); XT = K-major 128-row tiles of X
@@ -178,6 +180,10 @@ struct Progress {
 // written once with multimem.st to peerY[0] = the NVSwitch multicast mapping of Y (which includes this rank's Y)
 int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, int order, float *Y, int M, int N, int K,
                     long long ldy, int npeer, float *const *peerY, unsigned int *done, Progress *prog, int fused_tma = 0);
+// BCSR decode shape (decode_bcsr.cu): *handled = 0 outside its limits
+int bcsr_decode(tsg_bcsr *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy, int *handled);
+// decode shape (M < TSG_SKINNY_M): rows of X in shared memory, warp per column (decode_tcsc.cu)
+int tcsc_decode(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy, int *handled);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
 int transpose_x_tiles(const float *X, float *XT, int M, int K);
 }  // namespace tsg

@@ -3,7 +3,10 @@
 Bars: b_row_start / b_col_idx bit-exact and b_values bit-exact against the reference's golden vectors (every golden
 case has no empty block-row, where the reference's row pointers are well defined); Y of bcsr_sgemm_basic / _avx /
 _avx2 bit-exact against the oracle (ascending-k accumulation from the bias, one rounding per term, ternary blocks =>
-x*val exact); bcsr_sgemm_prelu_* equal PReLU of that, i.e. the north-star math, not the reference's literal loop."""
+x*val exact); bcsr_sgemm_prelu_* equal PReLU of that, i.e. the north-star math, not the reference's literal loop.
+Decode shapes (M < 32, block width 4/8/16) run the tree-summing decode kernel by default (csrc/decode_bcsr.cu): there the bar is
+the tolerance contract, max |y - y_exact| <= 1e-5 * max(|y_exact|, 1), with the bit-exact kernels (tsg_bcsr_set_kernel(2))
+checked next to it on the same inputs."""
 import numpy as np
 import pytest
 
@@ -11,6 +14,14 @@ import __graft_entry__ as ge
 from tests.golden.make_golden import BCSR_CASES
 
 pytestmark = pytest.mark.gpu
+
+
+def _decode_shape(M, c):
+    return M < 32 and c in (4, 8, 16)
+
+
+def _close(y, exact):
+    return float(np.max(np.abs(y - exact) / np.maximum(np.abs(exact), 1.0))) <= 1e-5
 
 
 @pytest.fixture(scope="module")
@@ -33,8 +44,13 @@ def test_bcsr_golden(t, port, golden, case):
         assert np.array_equal(w.b_col_idx, golden[f"bcsr.{name}.col_idx"])
         assert np.array_equal(w.b_values, golden[f"bcsr.{name}.values"])
         Xi, B2 = port.gen_intvalued((M, K), seed + 1, 512), np.full(N, 2.0, np.float32)
-        assert np.array_equal(t.bcsr_sgemm_basic(Xi, w, B2, N), golden[f"bcsr.{name}.int.Y_bias"])
+        assert np.array_equal(t.bcsr_sgemm_basic(Xi, w, B2, N), golden[f"bcsr.{name}.int.Y_bias"])  # integer-valued: exact in any order
         Xu, Bu = port.gen_uniform((M, K), seed + 1), port.gen_uniform((N,), seed + 2)
+        if _decode_shape(M, c):  # default = decode kernel: tolerance; then the bit-exact kernels for everything below
+            assert _close(t.bcsr_sgemm_basic(Xu, w, Bu, N), golden[f"bcsr.{name}.real.basic"])
+            assert _close(t.bcsr_sgemm_prelu_basic(Xu, w, Bu, 0.2, N), np.where(golden[f"bcsr.{name}.real.basic"] < 0,
+                                                                           np.float32(0.2) * golden[f"bcsr.{name}.real.basic"], golden[f"bcsr.{name}.real.basic"]))
+            t.bcsr_set_kernel(2)
         y = t.bcsr_sgemm_basic(Xu, w, Bu, N)
         assert np.array_equal(y, golden[f"bcsr.{name}.real.basic"])
         assert np.array_equal(t.bcsr_sgemm_avx(Xu, w, Bu, N), y) and np.array_equal(t.bcsr_sgemm_avx2(Xu, w, Bu, N), y)
@@ -45,6 +61,7 @@ def test_bcsr_golden(t, port, golden, case):
         lit = golden[f"bcsr.{name}.real.prelu_basic_literal"]
         print(f"{name}: max |PReLU(X*W+b) - reference literal loop| = {np.abs(yp - lit).max():.3e}")
     finally:
+        t.bcsr_set_kernel(0)
         w.free()
 
 
@@ -60,9 +77,37 @@ def test_bcsr_vs_oracle(t, port, shape):
         assert w.k == wo.k and np.array_equal(w.b_row_start, wo.b_row_start) and np.array_equal(w.b_col_idx, wo.b_col_idx)
         assert np.array_equal(w.b_values, wo.b_values)
         X, B = port.gen_uniform((M, K), seed + 1), port.gen_uniform((N,), seed + 2)
+        if _decode_shape(M, c):
+            assert _close(t.bcsr_sgemm_basic(X, w, B, N), port.bcsr_sgemm_basic(X, wo, B, N))
+            assert _close(t.bcsr_sgemm_prelu_basic(X, w, B, 0.2, N), port.bcsr_sgemm_prelu_math(X, wo, B, 0.2, N))
+            t.bcsr_set_kernel(2)
         y = t.bcsr_sgemm_basic(X, w, B, N)
         assert np.array_equal(y, port.bcsr_sgemm_basic(X, wo, B, N))
         assert np.array_equal(t.bcsr_sgemm_prelu_basic(X, w, B, 0.2, N), port.bcsr_sgemm_prelu_math(X, wo, B, 0.2, N))
+    finally:
+        t.bcsr_set_kernel(0)
+        w.free()
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 2048, 1, 8, 1, 2, 31), (1, 4096, 4096, 1, 8, 1, 10, 32), (7, 1000, 520, 1, 8, 1, 2, 33), (31, 768, 256, 2, 4, 1, 4, 34),
+                                   (9, 640, 512, 1, 16, 1, 3, 35), (3, 96, 100, 8, 8, 1, 2, 36), (2, 20000, 64, 1, 8, 1, 2, 37)])
+def test_bcsr_decode_kernel(t, port, shape):
+    """the decode kernel on its own shapes (the first is the reference's only BCSR GEMM test, test_bcsr.cpp:13-17): tolerance
+    against the oracle's sequential result, exactness on integer-valued X, and agreement of all five entry points"""
+    M, K, N, r, c, num, den, seed = shape
+    Wd = port.gen_ternary(K, N, seed, num, den)
+    w = t.bcsr_from_dense(Wd, r, c)
+    wo = port.bcsr_from_dense(Wd, r, c)
+    try:
+        X, B = port.gen_uniform((M, K), seed + 1), port.gen_uniform((N,), seed + 2)
+        want = port.bcsr_sgemm_basic(X, wo, B, N)
+        y = t.bcsr_sgemm_basic(X, w, B, N)
+        assert _close(y, want), float(np.max(np.abs(y - want)))
+        assert np.array_equal(t.bcsr_sgemm_avx(X, w, B, N), y) and np.array_equal(t.bcsr_sgemm_avx2(X, w, B, N), y)  # deterministic
+        yp = t.bcsr_sgemm_prelu_basic(X, w, B, 0.2, N)
+        assert np.array_equal(yp, np.where(y < 0, np.float32(0.2) * y, y)) and np.array_equal(t.bcsr_sgemm_prelu_avx(X, w, B, 0.2, N), yp)
+        Xi, B2 = port.gen_intvalued((M, K), seed + 3, 512), np.full(N, 2.0, np.float32)
+        assert np.array_equal(t.bcsr_sgemm_basic(Xi, w, B2, N), port.bcsr_sgemm_basic(Xi, wo, B2, N))
     finally:
         w.free()
 

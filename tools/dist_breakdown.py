@@ -10,7 +10,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge  # noqa: E402
 
 rank, lr, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-os.environ.setdefault("NCCL_DEBUG", "WARN")
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 t = ge.load()
@@ -48,10 +47,21 @@ res["torch_bcast_X_64MB"] = timeit(lambda: dist.broadcast(X, src=0))
 res["tsg_barrier"] = timeit(lambda: D.barrier())
 Bl = B[c0:c0 + nc].contiguous()
 res["local_gemm_only(world=1 path)"] = timeit(lambda: t.lib().tsg_tcsc_gemm(W.h, t._ptr(X), t._ptr(Bl), 0.2, 1, 1, Y.data_ptr() + 4 * c0, M, nc, K, N))
-for mode in (4, 3, 2, 1, 0):
+modes = [int(m) for m in os.environ.get("TSG_BREAKDOWN_MODES", "5,3,2").split(",")]
+print_mc = D.has_multicast()
+for mode in modes:
+    if mode == 5 and not print_mc:
+        continue
     Yb = Y if mode else torch.empty((M, N), device="cuda")
     res[f"dist_gemm_mode{mode}_nobcast"] = timeit(lambda: D.gemm(W, X, B, Yb, N, a=0.2, use_prelu=True, root=-1, mode=mode))
     res[f"dist_gemm_mode{mode}_bcast"] = timeit(lambda: D.gemm(W, X, B, Yb, N, a=0.2, use_prelu=True, root=0, mode=mode))
+# exchange only: a W without non-zeros leaves the epilogue (bias + PReLU + store + exchange) and nothing else
+W0 = t.DeviceTcsc.from_dense(torch.zeros((K, nc), device="cuda"))
+for mode in modes:
+    if mode == 0 or (mode == 5 and not print_mc):
+        continue
+    res[f"exchange_only_mode{mode}(empty W)"] = timeit(lambda: D.gemm(W0, X, B, Y, N, a=0.2, use_prelu=True, root=-1, mode=mode))
+res["local_gemm_empty_W"] = timeit(lambda: t.lib().tsg_tcsc_gemm(W0.h, t._ptr(X), t._ptr(Bl), 0.2, 1, 1, Y.data_ptr() + 4 * c0, M, nc, K, N))
 # raw peer pushes, no compute: every rank pushes its slab to every peer, (a) strided 2-D copies into the row-major Y,
 # (b) the same bytes as contiguous 1-D copies, each on one stream per peer
 import ctypes as C
