@@ -309,3 +309,48 @@ def test_host_pointer_pipeline_large(t, port):
     y = t.tcsc_sgemm_optimized(X, w, B)
     assert np.array_equal(y, port.tcsc_sgemm_optimized(X, wo, B))
     w.free()
+
+
+# ---- opt-in TSG_ORDER_FAST: tolerance contract, integer-valued X exact, reference-named entry points behind the switch -----------
+@pytest.mark.parametrize("shape", [(4096, 4096, 4096, 1, 10, 42), (300, 1000, 520, 1, 2, 7), (128, 64, 40, 1, 3, 8), (64, 512, 512, 1, 2, 9), (257, 3000, 264, 1, 100, 10)])
+def test_fast_order(t, port, shape):
+    import torch
+    M, K, N, num, den, seed = shape
+    Wd = t.gen_ternary(K, N, seed, num, den)
+    w = t.DeviceTcsc.from_dense(Wd)
+    X, B = t.gen_uniform((M, K), seed + 1), t.gen_uniform((N,), seed + 2)
+    Yx, Yf = torch.empty((M, N), device="cuda"), torch.empty((M, N), device="cuda")
+    w.gemm(X, B, Yx, a=0.2, use_prelu=True, order=t.ORDER_BIAS_LAST)
+    w.gemm(X, B, Yf, a=0.2, use_prelu=True, order=t.ORDER_FAST)
+    mr = min(M, 64)
+    rel_fast, _ = t.verify_dense_f64(X, Wd, B, Yf, a=0.2, use_prelu=True, m0=0, mrows=mr)
+    rel_exact, _ = t.verify_dense_f64(X, Wd, B, Yx, a=0.2, use_prelu=True, m0=0, mrows=mr)
+    print(f"M{M} K{K} N{N}: fast order vs fp64 {rel_fast:.3e}; reference order vs fp64 {rel_exact:.3e}")
+    assert rel_fast <= max(TOL, rel_exact * (1 + 1e-6))  # never worse than the bar the exact order is held to
+    Xi, B2 = t.gen_intvalued((M, K), seed + 3, 512), torch.full((N,), 2.0, device="cuda")
+    w.gemm(Xi, B2, Yx, order=t.ORDER_BIAS_LAST)
+    w.gemm(Xi, B2, Yf, order=t.ORDER_FAST)
+    assert torch.equal(Yx, Yf)  # integer-valued: every order is exact
+    w.gemm(X, B, Yx, a=0.2, use_prelu=True, order=t.ORDER_BIAS_LAST)  # the two private streams coexist: exact order unchanged afterwards
+    wo = port.tcsc_from_dense(Wd.cpu().numpy())
+    rows = [0, M // 2, M - 1]
+    assert np.array_equal(Yx[rows].cpu().numpy(), port.tcsc_sgemm_prelu_basic(X[rows].cpu().numpy(), wo, B.cpu().numpy(), 0.2))
+    w.destroy()
+
+
+def test_fast_order_switch_for_reference_entry_points(t, port):
+    M, K, N = 96, 700, 300
+    Wd = port.gen_ternary(K, N, 77, 1, 4)
+    X, B = port.gen_uniform((M, K), 78), port.gen_uniform((N,), 79)
+    W, Wo = t.tcsc_from_dense(Wd), port.tcsc_from_dense(Wd)
+    exact = t.tcsc_sgemm_prelu_basic(X, W, B, 0.2)
+    assert np.array_equal(exact, port.tcsc_sgemm_prelu_basic(X, Wo, B, 0.2))
+    t.set_fast_order(True)
+    try:
+        fast = t.tcsc_sgemm_prelu_basic(X, W, B, 0.2)
+    finally:
+        t.set_fast_order(False)
+    y64 = port.tcsc_sgemm_f64(X, Wo, B, 0.2)
+    assert rel_err(fast, y64) <= max(TOL, rel_err(exact, y64))
+    assert np.array_equal(t.tcsc_sgemm_prelu_basic(X, W, B, 0.2), exact)  # switch off again: the reference's bits
+    W.free()
