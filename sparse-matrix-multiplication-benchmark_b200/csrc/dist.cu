@@ -88,6 +88,14 @@ __global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict_
     Y[e] = G[((size_t)p * M + m) * wmax + (n - c0.v[p])];
 }
 
+// root's X -> the multicast mapping of the symmetric X buffer: one read of X, one write that the NVSwitch replicates into every rank
+__global__ void __launch_bounds__(512) k_mc_broadcast(const float4 *__restrict__ src, float *__restrict__ mc, long long nvec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+
 }  // namespace tsg
 
 using namespace tsg;
@@ -165,11 +173,21 @@ struct tsg_dist {
     float *y_peer[TSG_MAX_PEERS] = {nullptr};
     // symmetric Y from the virtual-memory API with an NVSwitch multicast mapping on top (mode 5): a store to y_mc lands in
     // the Y of EVERY rank, so a finished tile leaves its GPU once instead of world-1 times
-    bool vmm = false;
-    size_t vmm_size = 0;
-    CUmemGenericAllocationHandle mem = 0, mc = 0, peer_mem[TSG_MAX_PEERS] = {0};
-    CUdeviceptr va_local = 0, va_mc = 0, va_peer[TSG_MAX_PEERS] = {0};
+    struct SymBuf {  // one symmetric buffer: this rank's physical memory, its multicast mapping, the peers' unicast mappings
+        bool vmm = false;
+        size_t vmm_size = 0;
+        CUmemGenericAllocationHandle mem = 0, mc = 0, peer_mem[TSG_MAX_PEERS] = {0};
+        CUdeviceptr va_local = 0, va_mc = 0, va_peer[TSG_MAX_PEERS] = {0};
+    };
+    SymBuf ysym;
     float *y_mc = nullptr;
+    // X broadcast through the switch (mode 5): root writes X once into the multicast mapping of a symmetric X buffer
+    SymBuf xsym;
+    size_t x_sym_bytes = 0;
+    float *x_sym = nullptr, *x_sym_mc = nullptr;
+    bool x_sym_failed = false;
+    cudaStream_t side = nullptr;  // copy-engine work that runs beside the GEMM kernel
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
     int *flag = nullptr;
     // host-buffer entry point: device copy of X assembled from the ranks' row blocks
     float *x_dev = nullptr;
@@ -236,34 +254,34 @@ static bool all_ranks_ok(tsg_dist *D, bool ok) {
     return h[1] == 0;
 }
 
-static void vmm_release(tsg_dist *D) {
+static void vmm_release(tsg_dist::SymBuf &S) {
     if (!g_drv.ok) return;
     for (int p = 0; p < TSG_MAX_PEERS; ++p) {
-        if (D->va_peer[p]) { g_drv.MemUnmap(D->va_peer[p], D->vmm_size); g_drv.MemAddressFree(D->va_peer[p], D->vmm_size); }
-        if (D->peer_mem[p]) g_drv.MemRelease(D->peer_mem[p]);
-        D->va_peer[p] = 0;
-        D->peer_mem[p] = 0;
+        if (S.va_peer[p]) { g_drv.MemUnmap(S.va_peer[p], S.vmm_size); g_drv.MemAddressFree(S.va_peer[p], S.vmm_size); }
+        if (S.peer_mem[p]) g_drv.MemRelease(S.peer_mem[p]);
+        S.va_peer[p] = 0;
+        S.peer_mem[p] = 0;
     }
-    if (D->va_mc) { g_drv.MemUnmap(D->va_mc, D->vmm_size); g_drv.MemAddressFree(D->va_mc, D->vmm_size); }
-    if (D->mc && D->mem) {
+    if (S.va_mc) { g_drv.MemUnmap(S.va_mc, S.vmm_size); g_drv.MemAddressFree(S.va_mc, S.vmm_size); }
+    if (S.mc && S.mem) {
         int dev = 0;
         cudaGetDevice(&dev);
         CUdevice cudev;
-        if (g_drv.DeviceGet(&cudev, dev) == CUDA_SUCCESS) g_drv.MulticastUnbind(D->mc, cudev, 0, D->vmm_size);
+        if (g_drv.DeviceGet(&cudev, dev) == CUDA_SUCCESS) g_drv.MulticastUnbind(S.mc, cudev, 0, S.vmm_size);
     }
-    if (D->va_local) { g_drv.MemUnmap(D->va_local, D->vmm_size); g_drv.MemAddressFree(D->va_local, D->vmm_size); }
-    if (D->mc) g_drv.MemRelease(D->mc);
-    if (D->mem) g_drv.MemRelease(D->mem);
-    D->va_mc = D->va_local = 0;
-    D->mc = D->mem = 0;
-    D->y_mc = nullptr;
-    D->vmm = false;
-    D->vmm_size = 0;
+    if (S.va_local) { g_drv.MemUnmap(S.va_local, S.vmm_size); g_drv.MemAddressFree(S.va_local, S.vmm_size); }
+    if (S.mc) g_drv.MemRelease(S.mc);
+    if (S.mem) g_drv.MemRelease(S.mem);
+    S.va_mc = S.va_local = 0;
+    S.mc = S.mem = 0;
+    S.vmm = false;
+    S.vmm_size = 0;
 }
 
 static void dist_unmap(tsg_dist *D) {
-    if (D->vmm) {
-        vmm_release(D);
+    if (D->ysym.vmm) {
+        vmm_release(D->ysym);
+        D->y_mc = nullptr;
         memset(D->y_peer, 0, sizeof D->y_peer);
         D->y_local = nullptr;
         D->y_bytes = 0;
@@ -297,7 +315,7 @@ static int steal_fd(int pid, int fd) {
 // multicast object shared by all ranks (created by rank 0, passed around as a POSIX file descriptor that the other
 // processes duplicate with pidfd_getfd), and every peer's memory mapped for unicast access (modes 1-3 keep working).
 // Collective.  Every step ends in a consensus, so either all ranks succeed or all fall back to cudaMalloc + CUDA IPC.
-static bool vmm_alloc_y(tsg_dist *D, size_t bytes) {
+static bool vmm_alloc(tsg_dist *D, tsg_dist::SymBuf &S, size_t bytes, bool want_peers) {
     if (getenv("TSG_DIST_NO_MULTICAST")) return false;  // same on every rank (environment of the launcher)
     bool ok = load_driver_api();
     int dev = 0;
@@ -329,23 +347,23 @@ static bool vmm_alloc_y(tsg_dist *D, size_t bytes) {
     if (gran == 0) gran = (size_t)2 << 20;
     const size_t size = (bytes + gran - 1) / gran * gran;
     mp.size = size;
-    D->vmm_size = size;
-    D->vmm = true;  // from here on dist_unmap releases whatever exists
+    S.vmm_size = size;
+    S.vmm = true;  // from here on dist_unmap releases whatever exists
     int my_mem_fd = -1, mc_fd = -1;
     // (1) physical memory + local mapping
-    if (ok) ok = g_drv.MemCreate(&D->mem, size, &ap, 0) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemCreate(&S.mem, size, &ap, 0) == CUDA_SUCCESS;
     CUmemAccessDesc acc;
     memset(&acc, 0, sizeof acc);
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = dev;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    if (ok) ok = g_drv.MemAddressReserve(&D->va_local, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_local, size, 0, D->mem, 0) == CUDA_SUCCESS &&
-                 g_drv.MemSetAccess(D->va_local, size, &acc, 1) == CUDA_SUCCESS;
-    if (ok) ok = g_drv.MemExportToShareableHandle(&my_mem_fd, D->mem, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemAddressReserve(&S.va_local, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(S.va_local, size, 0, S.mem, 0) == CUDA_SUCCESS &&
+                 g_drv.MemSetAccess(S.va_local, size, &acc, 1) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemExportToShareableHandle(&my_mem_fd, S.mem, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
     // (2) the multicast object: rank 0 creates and exports it
     if (ok && D->rank == 0)
-        ok = g_drv.MulticastCreate(&D->mc, &mp) == CUDA_SUCCESS &&
-             g_drv.MemExportToShareableHandle(&mc_fd, D->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+        ok = g_drv.MulticastCreate(&S.mc, &mp) == CUDA_SUCCESS &&
+             g_drv.MemExportToShareableHandle(&mc_fd, S.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
     // (3) everybody learns everybody's (pid, memory fd, multicast fd)
     struct Card { int pid, mem_fd, mc_fd, ok; };
     Card mine = {(int)getpid(), my_mem_fd, mc_fd, ok ? 1 : 0}, all[TSG_MAX_PEERS];
@@ -363,34 +381,39 @@ static bool vmm_alloc_y(tsg_dist *D, size_t bytes) {
     // (4) import the multicast object, join it, bind my memory, map it
     if (ok && D->rank != 0) {
         const int fd = steal_fd(all[0].pid, all[0].mc_fd);
-        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&D->mc, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&S.mc, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
         if (fd >= 0) close(fd);
     }
-    if (ok) ok = g_drv.MulticastAddDevice(D->mc, cudev) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MulticastAddDevice(S.mc, cudev) == CUDA_SUCCESS;
     ok = all_ranks_ok(D, ok);  // every device has joined before anybody binds
-    if (ok) ok = g_drv.MulticastBindMem(D->mc, 0, D->mem, 0, size, 0) == CUDA_SUCCESS;
-    if (ok) ok = g_drv.MemAddressReserve(&D->va_mc, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_mc, size, 0, D->mc, 0) == CUDA_SUCCESS &&
-                 g_drv.MemSetAccess(D->va_mc, size, &acc, 1) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MulticastBindMem(S.mc, 0, S.mem, 0, size, 0) == CUDA_SUCCESS;
+    if (ok) ok = g_drv.MemAddressReserve(&S.va_mc, size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(S.va_mc, size, 0, S.mc, 0) == CUDA_SUCCESS &&
+                 g_drv.MemSetAccess(S.va_mc, size, &acc, 1) == CUDA_SUCCESS;
     // (5) unicast mappings of every peer's memory
-    for (int p = 0; ok && p < D->world; ++p) {
+    for (int p = 0; ok && want_peers && p < D->world; ++p) {
         if (p == D->rank) continue;
         const int fd = steal_fd(all[p].pid, all[p].mem_fd);
-        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&D->peer_mem[p], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        ok = fd >= 0 && g_drv.MemImportFromShareableHandle(&S.peer_mem[p], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
         if (fd >= 0) close(fd);
-        if (ok) ok = g_drv.MemAddressReserve(&D->va_peer[p], size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(D->va_peer[p], size, 0, D->peer_mem[p], 0) == CUDA_SUCCESS &&
-                     g_drv.MemSetAccess(D->va_peer[p], size, &acc, 1) == CUDA_SUCCESS;
+        if (ok) ok = g_drv.MemAddressReserve(&S.va_peer[p], size, gran, 0, 0) == CUDA_SUCCESS && g_drv.MemMap(S.va_peer[p], size, 0, S.peer_mem[p], 0) == CUDA_SUCCESS &&
+                     g_drv.MemSetAccess(S.va_peer[p], size, &acc, 1) == CUDA_SUCCESS;
     }
     ok = all_ranks_ok(D, ok);  // also: nobody closes its descriptors before everybody has duplicated them
     if (my_mem_fd >= 0) close(my_mem_fd);
     if (mc_fd >= 0) close(mc_fd);
     if (!ok) {
-        vmm_release(D);
+        vmm_release(S);
         return false;
     }
-    D->y_local = reinterpret_cast<float *>(D->va_local);
-    D->y_mc = reinterpret_cast<float *>(D->va_mc);
+    return true;
+}
+
+static bool vmm_alloc_y(tsg_dist *D, size_t bytes) {
+    if (!vmm_alloc(D, D->ysym, bytes, true)) return false;
+    D->y_local = reinterpret_cast<float *>(D->ysym.va_local);
+    D->y_mc = reinterpret_cast<float *>(D->ysym.va_mc);
     D->y_bytes = bytes;
-    for (int p = 0; p < D->world; ++p) D->y_peer[p] = (p == D->rank) ? D->y_local : reinterpret_cast<float *>(D->va_peer[p]);
+    for (int p = 0; p < D->world; ++p) D->y_peer[p] = (p == D->rank) ? D->y_local : reinterpret_cast<float *>(D->ysym.va_peer[p]);
     return true;
 }
 
@@ -398,6 +421,10 @@ void tsg_dist_destroy(tsg_dist *D) {
     if (!D) return;
     cudaDeviceSynchronize();
     dist_unmap(D);
+    if (D->xsym.vmm) vmm_release(D->xsym);
+    if (D->side) cudaStreamDestroy(D->side);
+    if (D->ev_side[0]) cudaEventDestroy(D->ev_side[0]);
+    if (D->ev_side[1]) cudaEventDestroy(D->ev_side[1]);
     if (D->flag) cudaFree(D->flag);
     if (D->done) cudaFree(D->done);
     if (D->x_dev) cudaFree(D->x_dev);
@@ -495,8 +522,42 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         }
     } trace(trace_phases && D->world > 1, st, D->rank, mode);
     trace.mark(0);
-    // (1) X broadcast
-    if (root >= 0 && D->world > 1) TSG_NCCL(g_nccl.Broadcast(X, X, (size_t)M * K, ncclFloat32, root, D->comm, st));
+    // (1) X broadcast.  With a multicast-capable fabric (mode 5) root writes X ONCE into the multicast mapping of a symmetric X
+    //     buffer and every rank multiplies from its own copy; the copy back into the caller's X ("broadcast in place") runs on
+    //     a copy engine beside the GEMM kernel.  Otherwise ncclBroadcast.
+    const float *Xuse = X;
+    bool copy_back = false;
+    if (root >= 0 && D->world > 1) {
+        const size_t xbytes = (size_t)M * K * 4;
+        bool mc_bcast = (mode == 5) && D->y_mc && !D->x_sym_failed && !(xbytes & 15) && !(reinterpret_cast<uintptr_t>(X) & 15) &&
+                        !getenv("TSG_DIST_NCCL_BCAST");
+        if (mc_bcast && D->x_sym_bytes < xbytes) {  // (re)allocate: collective, every rank takes this branch in the same call
+            TSG_CUDA(cudaStreamSynchronize(st));
+            if (D->xsym.vmm) vmm_release(D->xsym);
+            D->x_sym = D->x_sym_mc = nullptr;
+            D->x_sym_bytes = 0;
+            if (vmm_alloc(D, D->xsym, xbytes, false)) {
+                D->x_sym = reinterpret_cast<float *>(D->xsym.va_local);
+                D->x_sym_mc = reinterpret_cast<float *>(D->xsym.va_mc);
+                D->x_sym_bytes = xbytes;
+            } else {
+                D->x_sym_failed = true;  // consensus inside vmm_alloc: the same on every rank
+                mc_bcast = false;
+            }
+        }
+        if (mc_bcast) {
+            if (D->rank == root) {
+                k_mc_broadcast<<<num_sms() * 2, 512, 0, st>>>(reinterpret_cast<const float4 *>(X), D->x_sym_mc, (long long)(xbytes / 16));
+                TSG_KERNEL_CHECK("k_mc_broadcast");
+            }
+            // ordering: the barrier that opens every exchange mode below follows root's kernel in root's stream, so no rank
+            // starts its GEMM before root's stores have been performed
+            Xuse = D->x_sym;
+            copy_back = (D->rank != root);
+        } else {
+            TSG_NCCL(g_nccl.Broadcast(X, X, (size_t)M * K, ncclFloat32, root, D->comm, st));
+        }
+    }
     trace.mark(1);
     if (D->world == 1) return tsg_tcsc_gemm(W_local, X, B, a, use_prelu, order, Y, M, N, K, N);
 
@@ -527,8 +588,20 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         if ((size_t)M * N * 4 > D->y_bytes) return set_error(TSG_EINVAL, "tsg_dist_gemm(mode 5): Y buffer too small");
         if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 5) needs M >= %d", TSG_SKINNY_M);
         float *peers[1] = {D->y_mc + col0};
-        TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y
-        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, X, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 1, peers, nullptr, nullptr, 3) : TSG_OK;
+        TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y (and root's X has arrived)
+        if (copy_back) {  // the caller's X on the non-root ranks: copy engine, concurrent with the GEMM kernel
+            if (!D->side) {
+                TSG_CUDA(cudaStreamCreateWithFlags(&D->side, cudaStreamNonBlocking));
+                TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[0], cudaEventDisableTiming));
+                TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[1], cudaEventDisableTiming));
+            }
+            TSG_CUDA(cudaEventRecord(D->ev_side[0], st));
+            TSG_CUDA(cudaStreamWaitEvent(D->side, D->ev_side[0], 0));
+            TSG_CUDA(cudaMemcpyAsync(X, D->x_sym, (size_t)M * K * 4, cudaMemcpyDeviceToDevice, D->side));
+            TSG_CUDA(cudaEventRecord(D->ev_side[1], D->side));
+        }
+        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, Xuse, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 1, peers, nullptr, nullptr, 3) : TSG_OK;
+        if (copy_back) TSG_CUDA(cudaStreamWaitEvent(st, D->ev_side[1], 0));
         const int rc2 = tsg_dist_barrier(D);
         return rc ? rc : rc2;
     }

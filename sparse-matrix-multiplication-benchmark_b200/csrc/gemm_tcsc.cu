@@ -624,7 +624,7 @@ struct UnitPlan {
 
 // unit decomposition: full 256-column tiles for as many complete rounds of the persistent grid as there are, the
 // left-over tiles cut into 2 or 4 narrower units each so that the last round is short (tail balancing)
-static UnitPlan plan_units(int M, int N, int sms) {
+static UnitPlan plan_units(int M, int N, int sms, int max_sub = 8) {
     UnitPlan u;
     u.mtiles = (M + TM - 1) / TM;
     u.ntiles = (N + CWMAX * NWARP - 1) / (CWMAX * NWARP);
@@ -642,7 +642,7 @@ static UnitPlan plan_units(int M, int N, int sms) {
         // still streams the whole X tile, so its time does not fall below the fill-bound floor (about 1/8 of a full unit)
         int best_sub = 1;
         double best = 1e30;
-        for (int sub = 1; sub <= 8; sub *= 2) {
+        for (int sub = 1; sub <= max_sub; sub *= 2) {
             const double unit = 1.0 / sub + 0.06;
             const double cost = (double)((U * sub + sms - 1) / sms) * (unit > 0.125 ? unit : 0.125);
             if (cost < best - 1e-9) { best = cost; best_sub = sub; }
@@ -844,7 +844,8 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     p.bar_off = (uint32_t)(ring_bytes + sep_bytes);
     const size_t smem_bytes = (size_t)p.bar_off + 96;
     if (smem_bytes > 232448) return set_error(TSG_EUNSUPPORTED, "tsg_tcsc_gemm: the gather stream of this matrix leaves no room for a separate output tile");
-    const UnitPlan up = plan_units(M, N, num_sms());
+    // the staged (TMA) epilogues write float4 pieces per warp: at least 4 columns per warp there
+    const UnitPlan up = plan_units(M, N, num_sms(), (fused_tma == 1 || fused_tma == 2) ? 4 : 8);
     p.ntiles = up.ntiles;
     p.units_full = up.units_full;
     p.sub = up.sub;
