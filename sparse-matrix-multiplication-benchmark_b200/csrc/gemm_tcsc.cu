@@ -617,6 +617,9 @@ static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, i
     return ws.release();
 }
 
+static thread_local int g_plan_sub_all = 0;
+void set_plan_sub_all(int sub) { g_plan_sub_all = sub; }
+
 // ---- host-side planning (pure arithmetic; also exported for the CPU tests: tsg_plan_*) ---------------------------------
 struct UnitPlan {
     int mtiles, ntiles, units_full, sub, units_total;
@@ -630,8 +633,11 @@ static UnitPlan plan_units(int M, int N, int sms, int max_sub = 8) {
     u.ntiles = (N + CWMAX * NWARP - 1) / (CWMAX * NWARP);
     const int U = u.mtiles * u.ntiles;
     u.units_full = (U / sms) * sms;
-    static const int force_sub = getenv("TSG_FORCE_SUB") ? atoi(getenv("TSG_FORCE_SUB")) : 0;  // experiment: every tile cut into 2 or 4 units
-    if (force_sub == 2 || force_sub == 4) {
+    // every tile cut into 2 or 4 units: the multi-GPU path at 8 ranks asks for it (smaller, more frequent tiles keep the fabric
+    // busy evenly while the kernel runs, dist.cu mode 5); TSG_FORCE_SUB does the same for experiments
+    static const int env_sub = getenv("TSG_FORCE_SUB") ? atoi(getenv("TSG_FORCE_SUB")) : 0;
+    const int force_sub = g_plan_sub_all ? g_plan_sub_all : env_sub;
+    if ((force_sub == 2 || force_sub == 4) && U >= sms) {
         u.units_full = 0;
         u.sub = force_sub;
         u.units_total = U * force_sub;

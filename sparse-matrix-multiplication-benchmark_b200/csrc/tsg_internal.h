@@ -184,6 +184,8 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
 int bcsr_decode(tsg_bcsr *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy, int *handled);
 // decode shape (M < TSG_SKINNY_M): rows of X in shared memory, warp per column (decode_tcsc.cu)
 int tcsc_decode(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy, int *handled);
+// planning override for the next tiled launches of this thread: cut every 256-column tile into `sub` units (0 = automatic)
+void set_plan_sub_all(int sub);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
 int transpose_x_tiles(const float *X, float *XT, int M, int K);
 }  // namespace tsg

@@ -354,3 +354,37 @@ def test_fast_order_switch_for_reference_entry_points(t, port):
     assert rel_err(fast, y64) <= max(TOL, rel_err(exact, y64))
     assert np.array_equal(t.tcsc_sgemm_prelu_basic(X, W, B, 0.2), exact)  # switch off again: the reference's bits
     W.free()
+
+
+# ---- the fp64 dense checker itself: it is what the full-size tests and bench.py lean on -----------------
+def test_verify_dense_f64_equals_numpy_and_catches_errors(t, port):
+    import torch
+    M, K, N, a = 70, 300, 90, 0.2
+    Wd = port.gen_ternary(K, N, 5, 1, 3)
+    X, B = port.gen_uniform((M, K), 6), port.gen_uniform((N,), 7)
+    y64 = X.astype(np.float64) @ Wd.astype(np.float64) + B.astype(np.float64)
+    y64 = np.where(y64 < 0, np.float64(np.float32(a)) * y64, y64)
+    Y = y64.astype(np.float32)  # the correctly rounded result: what remains is the fp32 rounding of Y itself
+    Xd, Wdd, Bd, Yd = (torch.from_numpy(v).cuda() for v in (X, Wd, B, Y))
+    rel, ab = t.verify_dense_f64(Xd, Wdd, Bd, Yd, a=a, use_prelu=True)
+    exp_ab = float(np.max(np.abs(Y.astype(np.float64) - y64)))
+    exp_rel = float(np.max(np.abs(Y.astype(np.float64) - y64) / np.maximum(np.abs(y64), 1.0)))
+    assert abs(ab - exp_ab) <= 1e-12 and abs(rel - exp_rel) <= 1e-12, (rel, exp_rel, ab, exp_ab)  # direct equality with numpy's fp64
+    assert rel < 1e-7
+    # negative: one wrong element must show up with its exact magnitude, wherever it is
+    for (m, n, delta) in ((0, 0, 1e-3), (M - 1, N - 1, 0.5), (33, 17, -2.0)):
+        Ybad = Yd.clone()
+        Ybad[m, n] += delta
+        rel_b, ab_b = t.verify_dense_f64(Xd, Wdd, Bd, Ybad, a=a, use_prelu=True)
+        want = abs(float(Ybad[m, n].item()) - y64[m, n])
+        assert abs(ab_b - want) <= 1e-9 and rel_b >= want / max(abs(y64[m, n]), 1.0) - 1e-9
+        # a row window that excludes the bad element does not see it
+        if m > 8:
+            rel_w, ab_w = t.verify_dense_f64(Xd, Wdd, Bd, Ybad, a=a, use_prelu=True, m0=0, mrows=8)
+            assert ab_w <= exp_ab + 1e-12
+    # without the activation, and with a pitch larger than N
+    Yp = torch.zeros((M, N + 6), device="cuda")
+    y_lin = X.astype(np.float64) @ Wd.astype(np.float64) + B.astype(np.float64)
+    Yp[:, :N] = torch.from_numpy(y_lin.astype(np.float32)).cuda()
+    rel_l, ab_l = t.verify_dense_f64(Xd, Wdd, Bd, Yp, use_prelu=False, ldy=N + 6)
+    assert abs(ab_l - float(np.max(np.abs(y_lin.astype(np.float32).astype(np.float64) - y_lin)))) <= 1e-12
