@@ -170,14 +170,16 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) { return
 // producer never waits for the bulk stores and a unit's stores drain while the next unit is being gathered.
 // MC (dist mode 5): the epilogue hands 32-row slices of the finished tile to three drain warps through two staging buffers of
 // their own; nothing overlays the stage ring and no CTA-wide barrier is left in the unit loop.
-template <bool TILE_SEP, bool MC = false>
+// FAST (TSG_ORDER_FAST): a stage carries the +1 AND the -1 slice of a chunk and one sweep over K does both; a template
+// parameter so that the exact-order instantiations carry none of its code.
+template <bool TILE_SEP, bool MC = false, bool FAST = false>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // a stage = X chunk + one stream area (exact orders: the +1 OR the -1 lists of the chunk) or two (TSG_ORDER_FAST: both)
     const uint32_t area_bytes = p.body_stage_bytes + CNT_BYTES + WOFF_BYTES;
-    const bool fast = (p.order == TSG_ORDER_FAST);
+    constexpr bool fast = FAST;
     const uint32_t stage_bytes = p.xstage_bytes + (fast ? 2u : 1u) * area_bytes;
-    const int npass = fast ? 1 : 2;
+    constexpr int npass = fast ? 1 : 2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.bar_off);
     uint64_t *empty = full + 2;
     uint64_t *epi = full + 4;  // fused epilogue: consumers -> producer "the output tile has left shared memory"
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 const uint32_t *woff_s = reinterpret_cast<const uint32_t *>(cnt_s + CNT_BYTES);
                 if (neg) gather_chunk<true>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
                 else gather_chunk<false>(acc, xbase, cnt_s, woff_s, body_s, warp, cw);
-                if (fast) {  // the chunk's -1 entries while the chunk is still resident: X streams through shared memory once
+                if constexpr (FAST) {  // the chunk's -1 entries while the chunk is still resident: X streams through shared memory once
                     const uint8_t *area = st + p.xstage_bytes + area_bytes;
                     gather_chunk<true>(acc, xbase, area + p.body_stage_bytes, reinterpret_cast<const uint32_t *>(area + p.body_stage_bytes + CNT_BYTES),
                                        reinterpret_cast<const uint32_t *>(area), warp, cw);
@@ -697,11 +699,15 @@ static void plan_progress(const UnitPlan &u, Progress *prog) {
 }
 
 static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, bool mc = false) {
+    const bool fast = (p.order == TSG_ORDER_FAST);
+    if (fast && tile_sep) return set_error(TSG_EUNSUPPORTED, "TSG_ORDER_FAST is not available with the separate-tile epilogue (dist mode 4)");
     static std::atomic<unsigned long long> attr_done{0};
     TSG_TRY(once_per_device(attr_done, [] {
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         return (int)TSG_OK;
     }));
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
@@ -711,8 +717,10 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, b
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream());
     }
-    if (mc) k_tcsc_gemm<false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    if (mc && fast) k_tcsc_gemm<false, true, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    else if (mc) k_tcsc_gemm<false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else if (tile_sep) k_tcsc_gemm<true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    else if (fast) k_tcsc_gemm<false, false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else k_tcsc_gemm<false><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_tcsc_gemm");
     if (g_profile) {

@@ -3,8 +3,9 @@
  * The reference hands callers plain structs with malloc'ed arrays (sparse/tcsc.h:6-17, sparse/bcsr.h:5-12) that they
  * may free(), rebuild at the same address or edit in place, and nothing tells the library.  A device mirror is
  * therefore only reused when the struct's dimensions, its array pointers AND a hash of the array contents still match.
- * Arrays of up to TSG_FP_FULL_WORDS 32-bit words are hashed completely; longer ones by their first and last 128 words
- * plus 512 evenly spaced words (a few microseconds per call); TSG_MIRROR_CHECK=full hashes everything,
+ * Arrays of up to TSG_FP_FULL_WORDS 32-bit words are hashed completely; longer ones by their first and last 64 words
+ * plus 128 evenly spaced words (about a microsecond per call for the four TCSC arrays: the reference's own shapes are a
+ * 15-microsecond kernel, so the check has to stay well below that); TSG_MIRROR_CHECK=full hashes everything,
  * TSG_MIRROR_CHECK=off trusts pointers and sizes alone.  Private. */
 #ifndef TSG_FINGERPRINT_H
 #define TSG_FINGERPRINT_H
@@ -13,7 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define TSG_FP_FULL_WORDS 1024
+#define TSG_FP_FULL_WORDS 256
 
 static inline uint64_t tsg_fp_mix(uint64_t h, uint64_t v) {
     h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
@@ -41,10 +42,10 @@ static inline uint64_t tsg_fp_words(const void *p, size_t nwords, uint64_t h) {
         for (size_t i = 0; i < nwords; ++i) h = tsg_fp_mix(h, w[i]);
         return h;
     }
-    for (size_t i = 0; i < 128; ++i) h = tsg_fp_mix(h, w[i]);
-    for (size_t i = nwords - 128; i < nwords; ++i) h = tsg_fp_mix(h, w[i]);
-    const size_t step = (nwords - 256) / 512 + 1;
-    for (size_t i = 128; i < nwords - 128; i += step) h = tsg_fp_mix(h, w[i]);
+    for (size_t i = 0; i < 64; ++i) h = tsg_fp_mix(h, w[i]);
+    for (size_t i = nwords - 64; i < nwords; ++i) h = tsg_fp_mix(h, w[i]);
+    const size_t step = (nwords - 128) / 128 + 1;
+    for (size_t i = 64; i < nwords - 64; i += step) h = tsg_fp_mix(h, w[i]);
     return h;
 }
 

@@ -74,7 +74,8 @@ def run(t, torch, hbm_peak, sm_max_mhz, quick=False):
     peaks = (hbm_peak, fadd_peak, 2 * fadd_peak)
     out = []
 
-    def tcsc_case(name, M, K, N, num, den, reps, seed=42):
+    def tcsc_case(name, M, K, N, num, den, reps, seed=42, order=None):
+        order = t.ORDER_BIAS_LAST if order is None else order
         Wd = t.gen_ternary(K, N, seed, num, den)
         W = t.DeviceTcsc.from_dense(Wd)
         del Wd
@@ -83,12 +84,19 @@ def run(t, torch, hbm_peak, sm_max_mhz, quick=False):
         Y = torch.empty((M, N), device="cuda")
         t.profile_enable(True)
         t.profile_read()
-        ms = _time_calls(torch, lambda: W.gemm(X, B, Y, a=ALPHA, use_prelu=True, order=t.ORDER_BIAS_LAST), reps)
+        ms = _time_calls(torch, lambda: W.gemm(X, B, Y, a=ALPHA, use_prelu=True, order=order), reps)
         kms, kn = t.profile_read()
         t.profile_enable(False)
         kernel_ms = (kms / kn) if kn else None  # tiled kernel only (includes the warm-up launches: same kernel)
         out.append(_bound_entry(name, ms, M, K, N, W.nnz, peaks, "tcsc", kernel_ms=kernel_ms,
-                                extra={"sparsity": 1 - num / den, "format": "TCSC", "function": "tcsc_sgemm_prelu_basic order"}))
+                                extra={"sparsity": 1 - num / den, "format": "TCSC",
+                                       "function": "tcsc_sgemm_prelu_basic order (bit-identical to the reference)" if order == t.ORDER_BIAS_LAST
+                                       else "TSG_ORDER_FAST (opt-in: one sweep over K, tolerance contract)"}))
+        if order == t.ORDER_FAST and M >= 32:  # the tolerance the opt-in order is held to, measured on a row slice
+            Wd2 = t.gen_ternary(K, N, seed, num, den)
+            rel, _ = t.verify_dense_f64(X, Wd2, B, Y, a=ALPHA, use_prelu=True, m0=0, mrows=min(M, 32))
+            out[-1]["max_rel_err_vs_f64"] = rel
+            del Wd2
         W.destroy()
 
     def bcsr_case(name, M, K, N, num, den, r, c, reps, seed=42):
@@ -125,11 +133,14 @@ def run(t, torch, hbm_peak, sm_max_mhz, quick=False):
             reps = 5 if M == 4096 else 20
             tcsc_case(f"cfg3 M{M} K4096 N4096 {tag} TCSC", M, 4096, 4096, num, den, reps)
             bcsr_case(f"cfg3 M{M} K4096 N4096 {tag} BCSR1x8", M, 4096, 4096, num, den, 1, 8, 3 if M == 4096 else 10)
+    # the opt-in single-sweep order on the headline shape (and below on configs[3])
+    tcsc_case("cfg2 M4096 K4096 N4096 90% TCSC fast order", 4096, 4096, 4096, 1, 10, 5, order=t.ORDER_FAST)
     # the reference's only BCSR GEMM test shape (test/test_bcsr.cpp:13-17)
     bcsr_case("test_bcsr.cpp M1 K512 N2048 50% BCSR1x8", 1, 512, 2048, 1, 2, 1, 8, 50)
     # configs[3]
     if not quick:
         tcsc_case("cfg4 M8192 K4096 N14336 66% TCSC", 8192, 4096, 14336, 1, 3, 3)
+        tcsc_case("cfg4 M8192 K4096 N14336 66% TCSC fast order", 8192, 4096, 14336, 1, 3, 3, order=t.ORDER_FAST)
 
     # conversion kernels: HBM bound, dense matrix read once
     def convert_case(name, K, N, num, den, reps, fmt="tcsc"):
