@@ -51,6 +51,7 @@ struct GemmParams {
     long long ldy;
     int M, N, K;
     int kc, nchunk, ncols_pad, ngroup;
+    int nstage;                  // depth of the shared-memory ring (2 or 3)
     int mtiles, ntiles;          // ntiles = number of 256-column tiles
     int units_full, units_total, sub;  // unit decomposition, see decode_unit()
     float a;
@@ -102,6 +103,25 @@ __device__ __forceinline__ void gather_word(float2 &a01, float2 &a23, uint32_t w
             }
         }
     }
+}
+
+// ---- thread-block cluster helpers (mid-size M: the CTAs that share a row tile of X receive each chunk by ONE multicast copy) ----
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> the same shared-memory offset of every CTA in `mask`, completing `bytes` on the mbarrier at the same offset of each
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "h"(mask)
+                 : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset of CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(
+                     smem_addr(bar)),
+                 "r"(rank)
+                 : "memory");
 }
 
 constexpr int CWMAX = 16;  // columns per warp in a full (256-column) tile; tail units use 8 or 4 (runtime `cw`)
@@ -172,7 +192,11 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams &p, int u) { return
 // their own; nothing overlays the stage ring and no CTA-wide barrier is left in the unit loop.
 // FAST (TSG_ORDER_FAST): a stage carries the +1 AND the -1 slice of a chunk and one sweep over K does both; a template
 // parameter so that the exact-order instantiations carry none of its code.
-template <bool TILE_SEP, bool MC = false, bool FAST = false>
+// CL > 1 (mid-size M, fewer tiles than SMs): a thread-block cluster of CL CTAs shares one 128-row tile of X and splits its 256
+// columns.  The cluster's leader fetches every X chunk ONCE with a multicast bulk copy into all CL shared memories (the chunk
+// is what every unit re-streams: L2 -> SM traffic falls by CL); the leader waits for all CL x 16 consumer warps (remote
+// mbarrier arrivals) before it overwrites a stage.  Stream slices stay per CTA.
+template <bool TILE_SEP, bool MC = false, bool FAST = false, int CL = 1>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // a stage = X chunk + one stream area (exact orders: the +1 OR the -1 lists of the chunk) or two (TSG_ORDER_FAST: both)
@@ -181,25 +205,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
     const uint32_t stage_bytes = p.xstage_bytes + (fast ? 2u : 1u) * area_bytes;
     constexpr int npass = fast ? 1 : 2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.bar_off);
-    uint64_t *empty = full + 2;
-    uint64_t *epi = full + 4;  // fused epilogue: consumers -> producer "the output tile has left shared memory"
-    unsigned int *tiles_done = reinterpret_cast<unsigned int *>(full + 5);  // multicast epilogue: compute-warp arrivals, monotonic
+    uint64_t *empty = full + 3;
+    uint64_t *epi = full + 6;  // fused epilogue: consumers -> producer "the output tile has left shared memory"
+    unsigned int *tiles_done = reinterpret_cast<unsigned int *>(full + 7);  // multicast epilogue: compute-warp arrivals, monotonic
+    uint64_t *xempty = full + 8;  // cluster variant, meaningful on the leader: stage s released by the consumers of ALL CTAs
+    const uint32_t nstage = (uint32_t)p.nstage;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // work distribution: CL == 1 walks the unit list; a cluster walks the tiles and its CTAs take the CL column parts of each
+    const int crank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
+    const int u_first = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int u_step = (CL > 1) ? (int)(gridDim.x / CL) : (int)gridDim.x;
+    const int u_end = (CL > 1) ? p.mtiles * p.ntiles : p.units_total;
+    auto unit_of = [&](int u) {
+        if constexpr (CL > 1) {
+            Unit r;
+            r.mt = u / p.ntiles;
+            r.cw = CWMAX / CL;
+            r.n0 = (u % p.ntiles) * (CWMAX * NWARP) + crank * (r.cw * NWARP);
+            return r;
+        } else {
+            return decode_unit(p, u);
+        }
+    };
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], NWARP);
-        mbar_init(&empty[1], NWARP);
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], NWARP);
+            mbar_init(&xempty[i], NWARP * CL);
+        }
         mbar_init(epi, NWARP);
         *tiles_done = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // every CTA's barriers exist before anybody arrives on them remotely
 
     if (warp >= NWARP) {
         // ===== producer warpgroup: hands its registers to the compute warpgroups; one thread feeds the two-stage ring =====
-        if (MC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER_MC));
+        if (MC || CL > 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER_MC));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
         if (MC && warp > NWARP) {
             // ===== drain warps (multicast epilogue, dist.cu mode 5): once the 16 compute warps have stored a unit's tile into the
@@ -231,17 +275,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
             return;
         }
         if (warp == NWARP && lane == 0) {
-            uint32_t it = 0, uidx = 0;
-            for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++uidx) {
-                const Unit un = decode_unit(p, u);
+            uint32_t s = 0, ph = 0, uidx = 0;  // ring position: stage s, phase parity ph of its barriers
+            for (int u = u_first; u < u_end; u += u_step, ++uidx) {
+                const Unit un = unit_of(u);
                 const int tn = un.cw * NWARP;
                 // fused epilogue: the previous unit's output tile overlays the stage ring until its bulk stores have read it
-                if (!TILE_SEP && !MC && p.fused_tma && uidx > 0) mbar_wait(epi, (uidx - 1) & 1u);
+                if (!TILE_SEP && !MC && p.fused_tma && uidx > 0) mbar_wait_relaxed(epi, (uidx - 1) & 1u);
                 const uint32_t woff_copy = (uint32_t)(((tn / 8 + 1) * 4 + 15) & ~15);
                 for (int pass = 0; pass < npass; ++pass) {
-                    for (int c = 0; c < p.nchunk; ++c, ++it) {
-                        const uint32_t s = it & 1u;
-                        mbar_wait(&empty[s], ((it >> 1) & 1u) ^ 1u);
+                    for (int c = 0; c < p.nchunk; ++c) {
+                        mbar_wait_relaxed(&empty[s], ph ^ 1u);
+                        if (CL > 1 && crank == 0) mbar_wait_relaxed(&xempty[s], ph ^ 1u);  // ... and by every other CTA of the cluster
                         uint8_t *st = smem + (size_t)s * stage_bytes;
                         const int rows = min(p.kc, p.K - c * p.kc);
                         const uint32_t xbytes = (uint32_t)rows * (TM * 4);
@@ -257,7 +301,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                             total += bbytes[q] + tn + woff_copy;
                         }
                         mbar_arrive_expect_tx(&full[s], total);
-                        bulk_g2s(st, p.XT + ((size_t)un.mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
+                        if constexpr (CL > 1) {  // the leader's copy lands in every CTA and completes xbytes on every CTA's full[s]
+                            if (crank == 0) bulk_g2s_multicast(st, p.XT + ((size_t)un.mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s], (uint16_t)((1u << CL) - 1u));
+                        } else {
+                            bulk_g2s(st, p.XT + ((size_t)un.mt * p.K + (size_t)c * p.kc) * TM, xbytes, &full[s]);
+                        }
                         for (int q = 0; q < nareas; ++q) {
                             const int plane = (fast ? q : pass) * p.nchunk + c;
                             uint8_t *area = st + p.xstage_bytes + (size_t)q * area_bytes;
@@ -265,20 +313,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                             bulk_g2s(area + p.body_stage_bytes, p.cnt + (size_t)plane * p.ncols_pad + un.n0, tn, &full[s]);
                             bulk_g2s(area + p.body_stage_bytes + CNT_BYTES, p.woff + gidx[q], woff_copy, &full[s]);
                         }
+                        if (++s == nstage) { s = 0; ph ^= 1u; }
                     }
                 }
             }
         }
+        if constexpr (CL > 1) cluster_sync_all();  // nobody leaves while a neighbour may still arrive on its barriers
         return;
     }
 
     // ===== consumers: 16 warps x cw columns, 4 rows per lane =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
     float2 acc[CWMAX][2];
-    uint32_t it = 0;
+    uint32_t s = 0, ph = 0;  // ring position of this warp
     const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
-        const Unit un = decode_unit(p, u);
+    for (int u = u_first; u < u_end; u += u_step) {
+        const Unit un = unit_of(u);
         const int cw = un.cw;
         const int nbase = un.n0 + warp * cw;
         const int mbase = un.mt * TM + lane;  // lane l holds rows l, l+32, l+64, l+96 of the tile (XT position 4l+v)
@@ -307,9 +357,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                 }
             }
             const bool neg = (pass == 1) && (p.order != TSG_ORDER_SPLIT);
-            for (int c = 0; c < p.nchunk; ++c, ++it) {
-                const uint32_t s = it & 1u;
-                mbar_wait(&full[s], (it >> 1) & 1u);
+            for (int c = 0; c < p.nchunk; ++c) {
+                mbar_wait(&full[s], ph);
                 const uint8_t *st = smem + (size_t)s * stage_bytes;
                 const uint32_t xbase = smem_addr(st) + lane * 16 - TM * 4;  // entries are k+1: fold the -512 in here
                 const uint32_t *body_s = reinterpret_cast<const uint32_t *>(st + p.xstage_bytes);
@@ -323,7 +372,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
                                        reinterpret_cast<const uint32_t *>(area), warp, cw);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) {
+                    mbar_arrive(&empty[s]);
+                    if constexpr (CL > 1) mbar_arrive_remote(&xempty[s], 0u);
+                }
+                if (++s == nstage) { s = 0; ph ^= 1u; }
             }
         }
         // ---- fused epilogue: bias, PReLU, store (and, on the multi-GPU path, the same store into every peer's Y) ----
@@ -415,6 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tcsc_gemm(const GemmParams p) {
         }
     }
     if (!MC && p.fused_tma && tid < TM) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all row stores have been performed
+    if constexpr (CL > 1) cluster_sync_all();
 }
 
 // ---- X (M x K row-major) -> XT[mtile][k][128], rows >= M zero ----------------------------------------------------------
@@ -698,7 +752,32 @@ static void plan_progress(const UnitPlan &u, Progress *prog) {
     }
 }
 
-static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, bool mc = false) {
+template <bool FAST, int CL>
+static int launch_cluster(const GemmParams &p, size_t smem_bytes, int tiles, cudaStream_t st) {
+    // as many clusters as tiles, capped by what the device can co-schedule (a cluster of 4 cannot use every SM: GPC granularity)
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(CL * (tiles > 0 ? tiles : 1));
+    int max_clusters = 0;
+    TSG_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, k_tcsc_gemm<false, false, FAST, CL>, &cfg));
+    if (max_clusters < 1) return set_error(TSG_EUNSUPPORTED, "no cluster of %d CTAs fits this device", CL);
+    const int nclusters = tiles < max_clusters ? tiles : max_clusters;
+    cfg.gridDim = dim3(CL * nclusters);
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, k_tcsc_gemm<false, false, FAST, CL>, p));
+    return TSG_OK;
+}
+
+// cl: 1 = one CTA per unit; 2 / 4 = thread-block clusters that share a row tile of X (mid-size M)
+static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, bool mc = false, int cl = 1) {
     const bool fast = (p.order == TSG_ORDER_FAST);
     if (fast && tile_sep) return set_error(TSG_EUNSUPPORTED, "TSG_ORDER_FAST is not available with the separate-tile epilogue (dist mode 4)");
     static std::atomic<unsigned long long> attr_done{0};
@@ -708,6 +787,10 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, b
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TSG_CUDA(cudaFuncSetAttribute(k_tcsc_gemm<false, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         return (int)TSG_OK;
     }));
     const int grid = p.units_total < num_sms() ? p.units_total : num_sms();
@@ -717,7 +800,13 @@ static int launch_tiled(const GemmParams &p, size_t smem_bytes, bool tile_sep, b
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream());
     }
-    if (mc && fast) k_tcsc_gemm<false, true, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
+    if (cl > 1 && !mc && !tile_sep) {
+        const int tiles = p.mtiles * p.ntiles;
+        int rc;
+        if (cl == 2) rc = fast ? launch_cluster<true, 2>(p, smem_bytes, tiles, stream()) : launch_cluster<false, 2>(p, smem_bytes, tiles, stream());
+        else rc = fast ? launch_cluster<true, 4>(p, smem_bytes, tiles, stream()) : launch_cluster<false, 4>(p, smem_bytes, tiles, stream());
+        if (rc != TSG_OK) return rc;
+    } else if (mc && fast) k_tcsc_gemm<false, true, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else if (mc) k_tcsc_gemm<false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else if (tile_sep) k_tcsc_gemm<true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
     else if (fast) k_tcsc_gemm<false, false, true><<<grid, NTHREADS, smem_bytes, stream()>>>(p);
@@ -837,7 +926,10 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     constexpr int kTileBytes = TM * TILE_PITCH * 4;
     const int sep_bytes = tile_sep ? kTileBytes : 0;  // shared memory behind the ring that is not part of it
     const bool fast = (order == TSG_ORDER_FAST);
-    TSG_TRY(build_kstream(W, sep_bytes, fast ? 2 : 1));
+    // ring depth: 3 shorter stages let a warp run up to two chunks ahead of the slowest one (TSG_STAGES=2|3; the overlay epilogues keep 2)
+    static const int env_stages = getenv("TSG_STAGES") ? atoi(getenv("TSG_STAGES")) : 2;
+    const int nstage = (env_stages == 3 && fused_tma != 1 && fused_tma != 2) ? 3 : 2;
+    TSG_TRY(build_kstream(W, sep_bytes, fast ? 2 : 1, nstage));
     const KStream &ks = fast ? W->ks_fast : W->ks;
     GemmParams p;
     p.mtiles = (M + TM - 1) / TM;
@@ -852,11 +944,12 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     for (int q = 0; q < TSG_MAX_PEERS; ++q) p.peerY[q] = (q < npeer) ? peerY[q] : nullptr;
     p.xstage_bytes = (uint32_t)ks.kc * TM * 4;
     p.body_stage_bytes = ((uint32_t)ks.max_tile_words * 4 + 15) & ~15u;
-    size_t ring_bytes = 2 * ((size_t)p.xstage_bytes + (fast ? 2 : 1) * (size_t)(p.body_stage_bytes + CNT_BYTES + WOFF_BYTES));
+    p.nstage = nstage;
+    size_t ring_bytes = (size_t)nstage * ((size_t)p.xstage_bytes + (fast ? 2 : 1) * (size_t)(p.body_stage_bytes + CNT_BYTES + WOFF_BYTES));
     if (fused_tma == 1 && ring_bytes < (size_t)kTileBytes) ring_bytes = (size_t)kTileBytes;  // tiny K: the tile is the larger one
     p.tile_off = sep_bytes ? (uint32_t)ring_bytes : 0u;
     p.bar_off = (uint32_t)(ring_bytes + sep_bytes);
-    const size_t smem_bytes = (size_t)p.bar_off + 96;
+    const size_t smem_bytes = (size_t)p.bar_off + 128;
     if (smem_bytes > 232448) return set_error(TSG_EUNSUPPORTED, "tsg_tcsc_gemm: the gather stream of this matrix leaves no room for a separate output tile");
     // the staged (TMA) epilogues write float4 pieces per warp: at least 4 columns per warp there
     const UnitPlan up = plan_units(M, N, num_sms(), (fused_tma == 1 || fused_tma == 2) ? 4 : 8);
@@ -873,7 +966,11 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
         p.ngroups = prog->ngroups;
         for (int i = 0; i <= prog->ngroups; ++i) p.gbound[i] = prog->gbound[i];
     }
-    int rc = launch_tiled(p, smem_bytes, tile_sep, mc);
+    // opt-in (TSG_CLUSTER=1): with fewer tiles than SMs the parts of a tile run as one thread-block cluster that receives X by multicast
+    static const int env_cluster = getenv("TSG_CLUSTER") ? atoi(getenv("TSG_CLUSTER")) : 0;  // measured: no faster (profiles/), L2 traffic / CL
+    int cl = 1;
+    if (env_cluster && !fused_tma && npeer == 0 && !done && up.units_full == 0 && up.sub >= 2 && K > 0) cl = up.sub >= 4 ? 4 : 2;
+    int rc = launch_tiled(p, smem_bytes, tile_sep, mc, cl);
     int rc2 = ws.release();
     return rc ? rc : rc2;
 }

@@ -103,14 +103,14 @@ static void free_kstream(KStream &ks) {
 static constexpr long long kSmemTotal = 232448 - 1024;
 static long long stage_bytes_for(int kc, int tile_words, int areas) { return (long long)kc * 512 + areas * ((long long)tile_words * 4 + 256 + 160); }
 
-int build_kstream(tsg_tcsc *W, int smem_reserved, int areas) {
+int build_kstream(tsg_tcsc *W, int smem_reserved, int areas, int nstage) {
     // smem_reserved: shared memory the kernel keeps for something else (the separate output tile of dist mode 4); the
     // chunk height is part of the stream's layout, so a different reservation means a different stream.
     // areas: stream slices per pipeline stage -- 1 for the exact orders (a stage holds the +1 OR the -1 lists of a chunk), 2 for
     // TSG_ORDER_FAST (both); the two layouts differ in the chunk height only and live side by side (ks / ks_fast)
     std::lock_guard<std::mutex> lk(W->mu);
     KStream &slot = (areas == 2) ? W->ks_fast : W->ks;
-    if (slot.built && slot.smem_reserved == smem_reserved) return TSG_OK;
+    if (slot.built && slot.smem_reserved == smem_reserved && slot.nstage == nstage) return TSG_OK;
     if (slot.built) {
         free_kstream(slot);
         slot = KStream();
@@ -125,12 +125,13 @@ int build_kstream(tsg_tcsc *W, int smem_reserved, int areas) {
     for (; kc > 16; kc -= 8) {
         double words_per_list = kc * density * 0.5 / 4.0 + 2.0;  // lists are padded to whole 4-word quads
         long long tile_words = (long long)(256 * words_per_list * 1.15) + 64;
-        if (2 * stage_bytes_for(kc, (int)tile_words, areas) <= kSmemBudget) break;
+        if (nstage * stage_bytes_for(kc, (int)tile_words, areas) <= kSmemBudget) break;
     }
     if (kc > K) kc = (K > 0) ? K : 1;
     for (int attempt = 0; attempt < 12; ++attempt) {
         KStream ks;
         ks.smem_reserved = smem_reserved;
+        ks.nstage = nstage;
         ks.kc = kc;
         ks.nchunk = (K + kc - 1) / kc;
         if (ks.nchunk < 1) ks.nchunk = 1;
@@ -201,7 +202,7 @@ int build_kstream(tsg_tcsc *W, int smem_reserved, int areas) {
             return set_error(TSG_ECUDA, "build_kstream: internal size bound violated (%u > %lld)", h_total, ks.body_words);
         }
         ks.max_tile_words = h_max;
-        if (2 * stage_bytes_for(kc, h_max, areas) <= kSmemBudget || kc <= 8) {
+        if (nstage * stage_bytes_for(kc, h_max, areas) <= kSmemBudget || kc <= 8) {
             ks.built = true;
             slot = ks;
             return TSG_OK;

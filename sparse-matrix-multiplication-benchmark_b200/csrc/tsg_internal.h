@@ -108,7 +108,8 @@ struct KStream {
     uint32_t *body = nullptr;  // packed words
     long long body_words = 0;  // capacity
     int max_tile_words = 0;    // max over planes and 256-column tiles of the tile's body words
-    int smem_reserved = 0;     // shared memory left out of the two-stage budget when kc was chosen (0 = the whole 227 KB)
+    int smem_reserved = 0;     // shared memory left out of the ring budget when kc was chosen (0 = the whole 227 KB)
+    int nstage = 2;            // ring depth kc was chosen for
     bool built = false;
 };
 
@@ -162,7 +163,7 @@ namespace tsg {
 int scan_exclusive_u32(const uint32_t *in, uint32_t *out, long long n, uint32_t *total_dev);
 // classify a pointer: 1 device (or managed), 0 host
 int is_device_pointer(const void *p);
-int build_kstream(tsg_tcsc *W, int smem_reserved = 0, int areas = 1);
+int build_kstream(tsg_tcsc *W, int smem_reserved = 0, int areas = 1, int nstage = 2);
 int bcsr_build_cols(tsg_bcsr *W);
 // ring kernel for BCSR (gemm_bcsr_ring.cu): *handled = 0 when the matrix does not fit its limits (caller falls back
 // to the plain kernel); XT = K-major 128-row tiles of X

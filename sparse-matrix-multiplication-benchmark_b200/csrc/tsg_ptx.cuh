@@ -27,6 +27,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+// the same for a thread that has time (the TMA producer): sleep between polls instead of spinning -- a hot try_wait loop took
+// 37 % of the issue slots of the scheduler that also hosts four gather warps (ncu, profiles/ncu_gemm_r02.md), and the stage
+// ring can only be released by the slowest warp
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "nanosleep.u32 128;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
