@@ -434,6 +434,64 @@ __global__ void __launch_bounds__(512, 1) k_ldgmix(const float *__restrict__ xg,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// F. dense regime: register-resident X strip (8 rows per lane, 2 x LDS.128 per k), warp-uniform predicated FADD2 per
+//    (k, column) from an 8-bit mask; does a predicated-off FADD2 cost one issue slot or the pipe's two cycles?
+//    THRESH: a mask bit is set when (hash & 255) < THRESH, i.e. per-sign density THRESH/256
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1) k_predfadd2(float *out, long long *cyc, int iters, int KC, uint32_t thresh) {
+    extern __shared__ __align__(16) float xs[];  // [KC][256]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < KC * 256; i += blockDim.x) xs[i] = (float)(i % 97) * 0.01f;
+    __shared__ uint32_t masks[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        uint32_t m = 0;
+        for (int j = 0; j < 8; ++j) {
+            uint32_t h = (i * 8 + j) * 2654435761u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            m |= ((h & 255u) < thresh ? 1u : 0u) << j;
+        }
+        masks[i] = m;
+    }
+    __syncthreads();
+    float2 acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[j][v] = make_float2(0.f, 0.f);
+    const uint32_t xb = smem_u32(xs) + lane * 32;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        const uint32_t *mp = masks + ((it * 16 + warp * 64) & 2047 & ~15);
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t m = mp[k];  // uniform address
+            float4 a, b;
+            const uint32_t addr = xb + ((it * 16 + k) & (KC - 1)) * 1024u;  // KC is a power of two
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr + 16));
+            const float2 x0 = make_float2(a.x, a.y), x1 = make_float2(a.z, a.w), x2 = make_float2(b.x, b.y), x3 = make_float2(b.z, b.w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (m & (1u << j)) {  // warp-uniform: predicated FADD2s
+                    acc[j][0] = __fadd2_rn(acc[j][0], x0);
+                    acc[j][1] = __fadd2_rn(acc[j][1], x1);
+                    acc[j][2] = __fadd2_rn(acc[j][2], x2);
+                    acc[j][3] = __fadd2_rn(acc[j][3], x3);
+                }
+            }
+        }
+    }
+    long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s += acc[j][v].x + acc[j][v].y;
+    if (s == 12345.678f) out[2] = s;
+    if (lane == 0) atomicMax((unsigned long long *)&cyc[blockIdx.x], (unsigned long long)(t1 - t0));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------------------
 static int g_nsm = 148;
@@ -495,6 +553,25 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&d_cyc, sizeof(long long) * NSM_MAX));
     const int it = 5000;
     // E
+    if (argc > 1 && argv[1][0] == 'F') {
+        const int KC = 64, smem = KC * 1024;
+        CK(cudaFuncSetAttribute(k_predfadd2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int iters = 4000;
+        for (uint32_t thresh : {13u, 26u, 43u, 64u, 85u, 128u, 256u}) {
+            // adds per warp per k: 8 rows x (popcount of the mask); expected popcount = 8 * thresh / 256
+            std::vector<uint32_t> hm(2048);
+            double bits = 0;
+            for (int i = 0; i < 2048; ++i)
+                for (int j = 0; j < 8; ++j) { uint32_t h = (i * 8 + j) * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; bits += ((h & 255u) < thresh); }
+            const double mean_pop = bits / 2048.0;
+            char nm[96], extra[96];
+            snprintf(nm, 96, "predfadd2_density%.3f", thresh / 256.0);
+            snprintf(extra, 96, ", \"mean_popcount_of_8\": %.3f", mean_pop);
+            run(nm, (double)iters * 16 * 16 * 8 * mean_pop, smem, [&] { k_predfadd2<<<g_nsm, 512, smem>>>(d_out, d_cyc, iters, KC, thresh); }, extra);
+        }
+        printf("{\"done\": true}\n");
+        return 0;
+    }
     if (argc > 1 && argv[1][0] == 'E') {
         const int KG = 96;  // 48 KB per SM in L1
         float *d_xg;
