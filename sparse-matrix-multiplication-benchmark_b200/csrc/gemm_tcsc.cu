@@ -494,8 +494,9 @@ __global__ void __launch_bounds__(256) k_transpose_x(const float *__restrict__ X
     }
 }
 
-int transpose_x_tiles(const float *X, float *XT, int M, int K) {
-    const int mtiles = (M + TM - 1) / TM;
+int transpose_x_tiles(const float *X, float *XT, int M, int K, int mtiles_min) {
+    int mtiles = (M + TM - 1) / TM;
+    if (mtiles < mtiles_min) mtiles = mtiles_min;  // tiles beyond M are written as zeros (the kernel pads rows >= M)
     dim3 grid((K + 31) / 32, mtiles);
     k_transpose_x<<<grid, 256, 0, stream()>>>(X, XT, M, K);
     TSG_KERNEL_CHECK("k_transpose_x");
@@ -636,6 +637,15 @@ __global__ void __launch_bounds__(256) k_tcsc_skinny(const float *__restrict__ X
 static thread_local int g_force_kernel = 0;
 static thread_local int g_profile = 0;
 static thread_local std::vector<cudaEvent_t> g_prof_events;
+
+void profile_mark(bool begin) {
+    if (!g_profile) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream());
+    g_prof_events.push_back(e);
+    (void)begin;
+}
 
 static int launch_skinny(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy) {
     static const int env_decode = getenv("TSG_DECODE") ? atoi(getenv("TSG_DECODE")) : 1;  // 0: the first skinny kernels (A/B runs)
@@ -922,6 +932,11 @@ int tcsc_gemm_peers(tsg_tcsc *W, const float *X, const float *B, float a, int us
     const bool skinny = npeer == 0 && !done && !fused_tma && ((g_force_kernel == 2) || (g_force_kernel == 0 && M < TSG_SKINNY_M));
     if (skinny) return launch_skinny(W, X, B, a, use_prelu, Y, M, N, K, ldy);
 
+    if (order == TSG_ORDER_FAST && npeer == 0 && !done && !fused_tma && M >= TSG_SKINNY_M) {  // dense regime of the opt-in order: multiplier form, every k
+        int handled = 0;
+        TSG_TRY(tcsc_gemm_dense_fast(W, X, B, a, use_prelu, Y, M, N, K, ldy, &handled));
+        if (handled) return TSG_OK;
+    }
     const bool tile_sep = (fused_tma == 2), mc = (fused_tma == 3);
     constexpr int kTileBytes = TM * TILE_PITCH * 4;
     const int sep_bytes = tile_sep ? kTileBytes : 0;  // shared memory behind the ring that is not part of it

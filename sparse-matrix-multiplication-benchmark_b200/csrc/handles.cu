@@ -142,6 +142,7 @@ void tsg_tcsc_destroy(tsg_tcsc *W) {
     dev_free(W->csp); dev_free(W->csn); dev_free(W->rip); dev_free(W->rin);
     dev_free(W->ks.cnt); dev_free(W->ks.woff); dev_free(W->ks.body);
     dev_free(W->ks_fast.cnt); dev_free(W->ks_fast.woff); dev_free(W->ks_fast.body);
+    dev_free(W->w2);
     delete W;
 }
 

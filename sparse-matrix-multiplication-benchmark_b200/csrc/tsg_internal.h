@@ -141,6 +141,7 @@ struct tsg_tcsc {
     int *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;  // device
     tsg::KStream ks;       // exact orders: one stream slice per pipeline stage
     tsg::KStream ks_fast;  // TSG_ORDER_FAST: the +1 and the -1 slice of a chunk share a stage (shorter chunks)
+    float2 *w2 = nullptr;  // TSG_ORDER_FAST, dense regime: W as {w, w} pairs, [tile of 128 columns][k][128] (gemm_dense_fast.cu); built lazily
     std::mutex mu;  // the private stream is built lazily inside the first GEMM: concurrent GEMMs on one handle serialise here
 };
 
@@ -188,5 +189,10 @@ int tcsc_decode(tsg_tcsc *W, const float *X, const float *B, float a, int use_pr
 // planning override for the next tiled launches of this thread: cut every 256-column tile into `sub` units (0 = automatic)
 void set_plan_sub_all(int sub);
 // X (M x K row-major) -> XT[ceil(M/128)][K][128] (zero padded rows)
-int transpose_x_tiles(const float *X, float *XT, int M, int K);
+// mtiles_min > ceil(M/128): additional all-zero tiles are written behind the real ones
+int transpose_x_tiles(const float *X, float *XT, int M, int K, int mtiles_min = 0);
+// dense regime of the opt-in fast order (gemm_dense_fast.cu); *handled = 0 when the matrix is too sparse for it
+int tcsc_gemm_dense_fast(tsg_tcsc *W, const float *X, const float *B, float a, int use_prelu, float *Y, int M, int N, int K, long long ldy, int *handled);
+// tsg_profile_enable: CUDA events around the dominant kernel of a call (begin / end) on the launching stream
+void profile_mark(bool begin);
 }  // namespace tsg

@@ -312,7 +312,8 @@ def test_host_pointer_pipeline_large(t, port):
 
 
 # ---- opt-in TSG_ORDER_FAST: tolerance contract, integer-valued X exact, reference-named entry points behind the switch -----------
-@pytest.mark.parametrize("shape", [(4096, 4096, 4096, 1, 10, 42), (300, 1000, 520, 1, 2, 7), (128, 64, 40, 1, 3, 8), (64, 512, 512, 1, 2, 9), (257, 3000, 264, 1, 100, 10)])
+@pytest.mark.parametrize("shape", [(4096, 4096, 4096, 1, 10, 42), (300, 1000, 520, 1, 2, 7), (128, 64, 40, 1, 3, 8), (64, 512, 512, 1, 2, 9), (257, 3000, 264, 1, 100, 10),
+                                   (257, 300, 100, 1, 2, 11), (32, 53, 129, 2, 3, 12)])  # the last two: dense regime (FFMA2 kernel), ragged rows / K / columns
 def test_fast_order(t, port, shape):
     import torch
     M, K, N, num, den, seed = shape

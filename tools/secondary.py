@@ -161,6 +161,8 @@ def run(t, torch, hbm_peak, sm_max_mhz, quick=False):
             bcsr_case(f"cfg3 M{M} K4096 N4096 {tag} BCSR1x8", M, 4096, 4096, num, den, 1, 8, 3 if M == 4096 else 10)
     # the opt-in single-sweep order on the headline shape (and below on configs[3])
     tcsc_case("cfg2 M4096 K4096 N4096 90% TCSC fast order", 4096, 4096, 4096, 1, 10, 5, order=t.ORDER_FAST)
+    if not quick:
+        tcsc_case("cfg3 M4096 K4096 N4096 50% TCSC fast order (dense FFMA2 kernel)", 4096, 4096, 4096, 1, 2, 5, order=t.ORDER_FAST)
     # the reference's only BCSR GEMM test shape (test/test_bcsr.cpp:13-17)
     bcsr_case("test_bcsr.cpp M1 K512 N2048 50% BCSR1x8", 1, 512, 2048, 1, 2, 1, 8, 50)
     # configs[3]
