@@ -14,6 +14,9 @@
 //                  finished row blocks with strided 2-D DMA copies while the kernel still runs.
 //   mode 3/4 fused through the TMA engine: every finished 128-row tile is staged in shared memory and written to the
 //                  local Y and every peer's Y with bulk async stores (mode 4: the tile has shared memory of its own).
+//   mode 5  fused through the NVSwitch: Y (and X) live in symmetric buffers from the virtual-memory API with a multicast
+//                  mapping on top; root writes X once with multimem.st and every finished tile is written once to the
+//                  multicast Y, the switch replicating it into every rank (default when the fabric supports it).
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded, else the system one), so the
 // library has no link-time NCCL dependency and loads on machines without it.
 #include <cuda.h>
@@ -158,6 +161,9 @@ bool load_driver_api() {
 }
 }  // namespace
 
+// D->flag: ints 0-3 are the barrier / consensus words, bytes [64, 64 + 16 * TSG_MAX_PEERS) the exchange area of vmm_alloc
+static const size_t kFlagBytes = 64 + 16 * TSG_MAX_PEERS;
+
 struct tsg_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -232,12 +238,12 @@ int tsg_dist_create(const unsigned char id128[128], int rank, int world, tsg_dis
         delete D;
         return set_error(TSG_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
     }
-    if (cudaMalloc(&D->flag, 32) != cudaSuccess) {
+    if (cudaMalloc(&D->flag, kFlagBytes) != cudaSuccess) {
         g_nccl.CommDestroy(D->comm);
         delete D;
         return set_error(TSG_ENOMEM, "cudaMalloc failed");
     }
-    cudaMemset(D->flag, 0, 32);
+    cudaMemset(D->flag, 0, kFlagBytes);
     *out = D;
     return TSG_OK;
 }
@@ -369,12 +375,11 @@ static bool vmm_alloc(tsg_dist *D, tsg_dist::SymBuf &S, size_t bytes, bool want_
     Card mine = {(int)getpid(), my_mem_fd, mc_fd, ok ? 1 : 0}, all[TSG_MAX_PEERS];
     memset(all, 0, sizeof all);
     {
-        Card *all_d = nullptr;
-        bool x = cudaMalloc(&all_d, sizeof(Card) * D->world) == cudaSuccess;
-        if (x) x = cudaMemcpyAsync(all_d + D->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        if (x) x = g_nccl.AllGather(all_d + D->rank, all_d, sizeof mine, /*ncclChar*/ 0, D->comm, st) == 0;  // every rank must take part
+        static_assert(sizeof(Card) == 16, "exchange area of D->flag is sized for 16-byte cards");
+        Card *all_d = reinterpret_cast<Card *>(reinterpret_cast<char *>(D->flag) + 64);  // no allocation here: every rank must reach the collective
+        bool x = cudaMemcpyAsync(all_d + D->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        x = (g_nccl.AllGather(all_d + D->rank, all_d, sizeof mine, /*ncclChar*/ 0, D->comm, st) == 0) && x;
         if (x) x = cudaMemcpyAsync(all, all_d, sizeof(Card) * D->world, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
-        if (all_d) cudaFree(all_d);
         ok = ok && x;
         for (int p = 0; p < D->world; ++p) ok = ok && all[p].ok;
     }
@@ -589,23 +594,29 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         if (M < TSG_SKINNY_M) return set_error(TSG_EUNSUPPORTED, "tsg_dist_gemm(mode 5) needs M >= %d", TSG_SKINNY_M);
         float *peers[1] = {D->y_mc + col0};
         TSG_TRY(tsg_dist_barrier(D));  // every rank has finished READING its previous Y (and root's X has arrived)
-        if (copy_back) {  // the caller's X on the non-root ranks: copy engine, concurrent with the GEMM kernel
-            if (!D->side) {
-                TSG_CUDA(cudaStreamCreateWithFlags(&D->side, cudaStreamNonBlocking));
-                TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[0], cudaEventDisableTiming));
-                TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[1], cudaEventDisableTiming));
+        // a failure between the two barriers must still reach the closing one, or the other ranks hang in theirs
+        auto body = [&]() -> int {
+            if (copy_back) {  // the caller's X on the non-root ranks: copy engine, concurrent with the GEMM kernel
+                if (!D->side) {
+                    TSG_CUDA(cudaStreamCreateWithFlags(&D->side, cudaStreamNonBlocking));
+                    TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[0], cudaEventDisableTiming));
+                    TSG_CUDA(cudaEventCreateWithFlags(&D->ev_side[1], cudaEventDisableTiming));
+                }
+                TSG_CUDA(cudaEventRecord(D->ev_side[0], st));
+                TSG_CUDA(cudaStreamWaitEvent(D->side, D->ev_side[0], 0));
+                TSG_CUDA(cudaMemcpyAsync(X, D->x_sym, (size_t)M * K * 4, cudaMemcpyDeviceToDevice, D->side));
+                TSG_CUDA(cudaEventRecord(D->ev_side[1], D->side));
             }
-            TSG_CUDA(cudaEventRecord(D->ev_side[0], st));
-            TSG_CUDA(cudaStreamWaitEvent(D->side, D->ev_side[0], 0));
-            TSG_CUDA(cudaMemcpyAsync(X, D->x_sym, (size_t)M * K * 4, cudaMemcpyDeviceToDevice, D->side));
-            TSG_CUDA(cudaEventRecord(D->ev_side[1], D->side));
-        }
-        // more than 4 ranks: half-width units -- the exchange (7/8 of Y inbound per rank) is as long as the GEMM itself, and it
-        // only hides behind it when finished tiles leave in a steady trickle (measured at 8 ranks: 1.40 -> 1.32 ms per step)
-        set_plan_sub_all(D->world > 4 ? 2 : 0);
-        const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, Xuse, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 1, peers, nullptr, nullptr, 3) : TSG_OK;
-        set_plan_sub_all(0);
-        if (copy_back) TSG_CUDA(cudaStreamWaitEvent(st, D->ev_side[1], 0));
+            // more than 4 ranks: half-width units -- the exchange (7/8 of Y inbound per rank) is as long as the GEMM itself, and
+            // it only hides behind it when finished tiles leave in a steady trickle (measured at 8 ranks: 1.40 -> 1.32 ms per
+            // step; at 4 ranks 1.209 -> 1.203, within noise)
+            set_plan_sub_all(D->world > 4 ? 2 : 0);
+            const int rc = (ncols > 0) ? tcsc_gemm_peers(W_local, Xuse, B + col0, a, use_prelu, order, Y + col0, M, ncols, K, N, 1, peers, nullptr, nullptr, 3) : TSG_OK;
+            set_plan_sub_all(0);
+            if (copy_back) TSG_CUDA(cudaStreamWaitEvent(st, D->ev_side[1], 0));
+            return rc;
+        };
+        const int rc = body();
         const int rc2 = tsg_dist_barrier(D);
         return rc ? rc : rc2;
     }

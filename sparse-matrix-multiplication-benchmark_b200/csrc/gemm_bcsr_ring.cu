@@ -217,18 +217,18 @@ struct BcsrRingParams {
     long long ldy;
     int M, N, K, r, br, ncov;  // ncov = bc * c: columns W covers
     int kcb, nchunk, ntile, units;
+    int full_units, sub;  // units [full_units, units) are dealt as `sub` column slices each (balances the last round over the SMs)
     float a;
     int use_prelu;
     uint32_t xstage_bytes, val_stage_bytes, hdr_stage_bytes;
 };
 
 // the block rows of this warp's block-columns inside the staged run, in (block-column, ascending k) order
-template <int C>
-__device__ __forceinline__ void bcsr_chunk(float (&acc)[BR_CW][4], const float *xs, const float *val_s, const uint8_t *hdr_s,
+template <int C, int NB>
+__device__ __forceinline__ void bcsr_chunk(float (&acc)[NB * C][4], const float *xs, const float *val_s, const uint8_t *hdr_s,
                                            const uint8_t *cn, uint32_t ei) {
-    constexpr int BPW = BR_CW / C;
 #pragma unroll
-    for (int b = 0; b < BPW; ++b) {
+    for (int b = 0; b < NB; ++b) {
         const int n = cn[b];
 #pragma unroll BR_UNROLL_N
         for (int t = 0; t < n; ++t, ++ei) {
@@ -257,6 +257,65 @@ __device__ __forceinline__ void bcsr_chunk(float (&acc)[BR_CW][4], const float *
     }
 }
 
+// one unit (or column slice `part` of one) on the consumer side: NB block-columns = NB*C output columns per warp, 4 rows per lane
+template <int C, int NB>
+__device__ __forceinline__ void ring_unit(const BcsrRingParams &p, uint8_t *smem, uint32_t stage_bytes, uint64_t *full, uint64_t *empty,
+                                          uint32_t &it, int u, int part, int warp, int lane) {
+    constexpr int BPW = BR_CW / C, W = NB * C;
+    const int mt = u / p.ntile, tile = u % p.ntile;
+    const int q0 = (part * BR_NWARP + warp) * NB;  // first block-column (inside the tile) of this warp
+    const int nbase = tile * BR_TN + q0 * C;
+    const int mbase = mt * BR_TM + lane;
+    const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0) && (W % 4 == 0);
+    float acc[W][4];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float b = (nbase + j < p.ncov) ? __ldg(p.B + nbase + j) : 0.f;  // bcsr.c:146-150: Y starts as the bias
+        acc[j][0] = b; acc[j][1] = b; acc[j][2] = b; acc[j][3] = b;
+    }
+    for (int c = 0; c < p.nchunk; ++c, ++it) {
+        const uint32_t s = it & 1u;
+        mbar_wait(&full[s], (it >> 1) & 1u);
+        const uint8_t *st = smem + (size_t)s * stage_bytes;
+        const float *xs = reinterpret_cast<const float *>(st) + lane * 4;
+        const float *val_s = reinterpret_cast<const float *>(st + p.xstage_bytes);
+        const uint8_t *hdr_s = st + p.xstage_bytes + p.val_stage_bytes;
+        const uint8_t *cnt_s = hdr_s + p.hdr_stage_bytes;
+        const uint32_t *wstart_s = reinterpret_cast<const uint32_t *>(cnt_s + BR_CNT_BYTES);
+        uint32_t ei = wstart_s[q0 / BPW];  // entries are stored per block-column in tile order; wstart marks every BPW-th column
+        if constexpr (NB < BPW) {
+            for (int j = (q0 / BPW) * BPW; j < q0; ++j) ei += cnt_s[j];
+        }
+        bcsr_chunk<C, NB>(acc, xs, val_s, hdr_s, cnt_s + q0, ei);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    const bool full_vec = vec_ok && (nbase + W <= p.ncov);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int m = mbase + 32 * v;
+        if (m >= p.M) continue;
+        float *yrow = p.Y + (size_t)m * p.ldy + nbase;
+        float out[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            float y = acc[j][v];
+            if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;
+            out[j] = y;
+        }
+        if (full_vec) {
+            if constexpr (W % 4 == 0) {
+#pragma unroll
+                for (int j = 0; j < W; j += 4) *reinterpret_cast<float4 *>(yrow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (nbase + j < p.ncov) yrow[j] = out[j];
+        }
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRingParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -279,7 +338,9 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BR_REGS_PRODUCER));
         if (warp == BR_NWARP && lane == 0) {
             uint32_t it = 0;
-            for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const int nvirt = p.full_units + (p.units - p.full_units) * p.sub;
+            for (int v = blockIdx.x; v < nvirt; v += gridDim.x) {
+                const int u = (v < p.full_units) ? v : p.full_units + (v - p.full_units) / p.sub;  // a slice stages the whole run of its unit
                 const int mt = u / p.ntile, tile = u % p.ntile;
                 for (int c = 0; c < p.nchunk; ++c, ++it) {
                     const uint32_t s = it & 1u;
@@ -307,53 +368,37 @@ __global__ void __launch_bounds__(BR_THREADS, 1) k_bcsr_gemm_ring(const BcsrRing
     // ===== consumers: 16 warps x 16 output columns, 4 rows per lane =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BR_REGS_COMPUTE));
     constexpr int BPW = BR_CW / C;
-    float acc[BR_CW][4];
     uint32_t it = 0;
-    const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const int mt = u / p.ntile, tile = u % p.ntile;
-        const int nbase = tile * BR_TN + warp * BR_CW;
-        const int mbase = mt * BR_TM + lane;
-#pragma unroll
-        for (int j = 0; j < BR_CW; ++j) {
-            const float b = (nbase + j < p.ncov) ? __ldg(p.B + nbase + j) : 0.f;  // bcsr.c:146-150: Y starts as the bias
-            acc[j][0] = b; acc[j][1] = b; acc[j][2] = b; acc[j][3] = b;
-        }
-        for (int c = 0; c < p.nchunk; ++c, ++it) {
-            const uint32_t s = it & 1u;
-            mbar_wait(&full[s], (it >> 1) & 1u);
-            const uint8_t *st = smem + (size_t)s * stage_bytes;
-            const float *xs = reinterpret_cast<const float *>(st) + lane * 4;
-            const float *val_s = reinterpret_cast<const float *>(st + p.xstage_bytes);
-            const uint8_t *hdr_s = st + p.xstage_bytes + p.val_stage_bytes;
-            const uint8_t *cnt_s = hdr_s + p.hdr_stage_bytes;
-            const uint32_t *wstart_s = reinterpret_cast<const uint32_t *>(cnt_s + BR_CNT_BYTES);
-            bcsr_chunk<C>(acc, xs, val_s, hdr_s, cnt_s + warp * BPW, wstart_s[warp]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        const bool full_vec = vec_ok && (nbase + BR_CW <= p.ncov);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int m = mbase + 32 * v;
-            if (m >= p.M) continue;
-            float *yrow = p.Y + (size_t)m * p.ldy + nbase;
-            float out[BR_CW];
-#pragma unroll
-            for (int j = 0; j < BR_CW; ++j) {
-                float y = acc[j][v];
-                if (p.use_prelu) y = (y < 0.0f) ? p.a * y : y;
-                out[j] = y;
+    const int nvirt = p.full_units + (p.units - p.full_units) * p.sub;
+    for (int v = blockIdx.x; v < nvirt; v += gridDim.x) {
+        if (v < p.full_units) {
+            ring_unit<C, BPW>(p, smem, stage_bytes, full, empty, it, v, 0, warp, lane);
+        } else {
+            const int q = v - p.full_units;
+            if constexpr (BPW >= 2) {
+                if (p.sub == 2) {
+                    ring_unit<C, BPW / 2>(p, smem, stage_bytes, full, empty, it, p.full_units + (q >> 1), q & 1, warp, lane);
+                    continue;
+                }
             }
-            if (full_vec) {
-#pragma unroll
-                for (int j = 0; j < BR_CW; j += 4) *reinterpret_cast<float4 *>(yrow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < BR_CW; ++j)
-                    if (nbase + j < p.ncov) yrow[j] = out[j];
-            }
+            ring_unit<C, BPW>(p, smem, stage_bytes, full, empty, it, p.full_units + q, 0, warp, lane);
         }
+    }
+}
+
+// Units are dealt round-robin over the persistent CTAs, so `units % sms` left-over units cost a whole extra round on a few SMs
+// while the rest idle (4096^3: 512 units on 148 SMs = 3.46 rounds, ncu: SMs active 85 % of the kernel).  Dealing the left-over
+// units as two column slices each (8 instead of 16 columns per warp; per-column arithmetic and its order unchanged) turns that
+// round into a half-length one whenever the slices still fit one round -- and doubles the CTAs of a problem smaller than the GPU.
+void bcsr_ring_plan(int units, int sms, int bpw, int *full_units, int *sub) {
+    const int rem = units % sms;
+    static const bool off = getenv("TSG_BCSR_NO_SPLIT") != nullptr;
+    if (off || bpw < 2 || rem == 0 || 2 * rem > sms) {
+        *full_units = units;
+        *sub = 1;
+    } else {
+        *full_units = units - rem;
+        *sub = 2;
     }
 }
 
@@ -364,7 +409,8 @@ static int launch_ring(const BcsrRingParams &p, size_t smem_bytes) {
         TSG_CUDA(cudaFuncSetAttribute(k_bcsr_gemm_ring<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM_MAX));
         return (int)TSG_OK;
     }));
-    const int grid = p.units < num_sms() ? p.units : num_sms();
+    const int nvirt = p.full_units + (p.units - p.full_units) * p.sub;
+    const int grid = nvirt < num_sms() ? nvirt : num_sms();
     k_bcsr_gemm_ring<C><<<grid, BR_THREADS, smem_bytes, stream()>>>(p);
     TSG_KERNEL_CHECK("k_bcsr_gemm_ring");
     return TSG_OK;
@@ -382,6 +428,7 @@ int bcsr_gemm_ring(tsg_bcsr *W, const float *XT, const float *B, float a, int us
     p.M = M; p.N = N; p.K = K; p.r = W->r; p.br = W->br; p.ncov = W->bc * W->c;
     p.kcb = bs.kcb; p.nchunk = bs.nchunk; p.ntile = bs.ntile;
     p.units = ((M + BR_TM - 1) / BR_TM) * bs.ntile;
+    bcsr_ring_plan(p.units, num_sms(), BR_CW / W->c, &p.full_units, &p.sub);
     p.a = a; p.use_prelu = use_prelu;
     p.xstage_bytes = (uint32_t)bs.kcb * W->r * BR_TM * 4;
     p.val_stage_bytes = (uint32_t)bs.max_run * W->c * 4;
@@ -400,3 +447,8 @@ int bcsr_gemm_ring(tsg_bcsr *W, const float *XT, const float *B, float a, int us
 }
 
 }  // namespace tsg
+
+// diagnostic (tests/test_plan.py): how the ring kernel deals `units` over `sms` persistent CTAs
+extern "C" void tsg_dbg_bcsr_ring_plan(int units, int sms, int bpw, int *full_units, int *sub) {
+    tsg::bcsr_ring_plan(units, sms, bpw, full_units, sub);
+}

@@ -80,3 +80,25 @@ def test_plan_rejects_bad_arguments(L):
     assert L.tsg_plan_units(0, 10, 148, C.byref(out)) != 0
     o = (C.c_int * 3)()
     assert L.tsg_plan_unit_at(128, 256, 148, 8, C.byref(o)) != 0  # one tile, fewer tiles than SMs: cut into 8 units (0..7)
+
+
+@pytest.mark.parametrize("sms", [148, 132, 7])
+@pytest.mark.parametrize("units", [1, 32, 74, 75, 148, 149, 222, 223, 512, 1024, 3000])
+@pytest.mark.parametrize("bpw", [1, 2, 16])
+def test_bcsr_ring_plan_never_lengthens_the_last_round(L, units, sms, bpw):
+    """gemm_bcsr_ring.cu: the left-over units of the last round are dealt as two column slices only when that shortens it."""
+    L.tsg_dbg_bcsr_ring_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tsg_dbg_bcsr_ring_plan.restype = None
+    fu, sub = C.c_int(), C.c_int()
+    L.tsg_dbg_bcsr_ring_plan(units, sms, bpw, C.byref(fu), C.byref(sub))
+    fu, sub = fu.value, sub.value
+    assert sub in (1, 2) and 0 <= fu <= units
+    if sub == 1:
+        assert fu == units
+    else:
+        assert bpw >= 2 and fu % sms == 0 and units - fu < sms and (units - fu) * 2 <= sms  # the slices fit ONE round
+    rounds_plain = -(-units // sms)
+    rounds_split = fu // sms + (-(-((units - fu) * sub) // sms)) / sub if sub == 2 else rounds_plain
+    assert rounds_split <= rounds_plain
+    if bpw >= 2 and 0 < units % sms <= sms // 2:
+        assert sub == 2 and rounds_split == rounds_plain - 0.5
