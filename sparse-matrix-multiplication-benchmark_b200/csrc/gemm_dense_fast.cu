@@ -20,6 +20,7 @@
 // TMA/mbarrier ring as in gemm_tcsc.cu, one producer thread, setmaxnreg hand-off.
 // W2 stream (private, built once per matrix from the TCSC arrays): W2[tile128][k][128] as float2 {w, w}.
 #include "tsg_internal.h"
+#include "tsg_f32x2.cuh"
 #include "tsg_ptx.cuh"
 
 namespace tsg {
@@ -63,14 +64,6 @@ int build_w2(tsg_tcsc *W) {
     }
     W->w2 = w2;
     return TSG_OK;
-}
-
-__device__ __forceinline__ float2 ffma2(float2 x, float2 w, float2 acc) {
-    float2 r;
-    asm("{ .reg .b64 a, b, c, d; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; mov.b64 c, {%6, %7}; fma.rn.f32x2 d, a, b, c; mov.b64 {%0, %1}, d; }"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(x.x), "f"(x.y), "f"(w.x), "f"(w.y), "f"(acc.x), "f"(acc.y));
-    return r;
 }
 
 __global__ void __launch_bounds__(DF_THREADS, 1) k_tcsc_dense_fast(const DenseFastParams p) {
