@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native sparse ternary GEMM  Y = PReLU(X*W + b)  (TCSC).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1|cfg5] [--dist-mode 0..4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1|cfg5] [--dist-mode 0..5]
                     [--no-secondary] [--no-cpu-baseline]
 
 Prints ONE JSON line on rank 0 (contract in the task statement).  Metric = BASELINE.json's "sparse GEMM GFLOP/s-equiv"
