@@ -92,11 +92,28 @@ __global__ void k_relayout_slabs(const float *__restrict__ G, float *__restrict_
 }
 
 // root's X -> the multicast mapping of the symmetric X buffer: one read of X, one write that the NVSwitch replicates into every rank
+// (U independent 16-byte loads in flight per thread before their stores)
+template <int U>
 __global__ void __launch_bounds__(512) k_mc_broadcast(const float4 *__restrict__ src, float *__restrict__ mc, long long nvec) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * (i + u * stride)), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+    }
+    for (; i < nvec; i += stride) {
         const float4 v = __ldg(src + i);
         asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(512) k_mc_broadcast_words(const float *__restrict__ src, float *__restrict__ mc, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(mc + i), "f"(__ldg(src + i)) : "memory");
 }
 
 }  // namespace tsg
@@ -534,8 +551,12 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
     bool copy_back = false;
     if (root >= 0 && D->world > 1) {
         const size_t xbytes = (size_t)M * K * 4;
-        bool mc_bcast = (mode == 5) && D->y_mc && !D->x_sym_failed && !(xbytes & 15) && !(reinterpret_cast<uintptr_t>(X) & 15) &&
-                        !getenv("TSG_DIST_NCCL_BCAST");
+        // one GPU writes through the multicast mapping at about 500 GB/s, NCCL's pipelined broadcast reaches 700 GB/s but needs
+        // 0.35 ms for 64 MB across 8 ranks (tools/bcast_probe.py, dist_breakdown.py): the switch wins on latency, NCCL on size
+        const char *max_mb = getenv("TSG_MC_BCAST_MAX_MB");  // read per call: the launcher's environment, the same on every rank
+        const size_t mc_bcast_max = (size_t)(max_mb ? atoll(max_mb) : 256) << 20;
+        // (the decision may only depend on what every rank knows: sizes and the environment, not this rank's pointer)
+        bool mc_bcast = (mode == 5) && D->y_mc && !D->x_sym_failed && !(xbytes & 15) && xbytes <= mc_bcast_max && !getenv("TSG_DIST_NCCL_BCAST");
         if (mc_bcast && D->x_sym_bytes < xbytes) {  // (re)allocate: collective, every rank takes this branch in the same call
             TSG_CUDA(cudaStreamSynchronize(st));
             if (D->xsym.vmm) vmm_release(D->xsym);
@@ -552,7 +573,15 @@ int tsg_dist_gemm(tsg_dist *D, tsg_tcsc *W_local, float *X, int root, const floa
         }
         if (mc_bcast) {
             if (D->rank == root) {
-                k_mc_broadcast<<<num_sms() * 2, 512, 0, st>>>(reinterpret_cast<const float4 *>(X), D->x_sym_mc, (long long)(xbytes / 16));
+                static const int unroll = getenv("TSG_MC_BCAST_UNROLL") ? atoi(getenv("TSG_MC_BCAST_UNROLL")) : 1;  // diagnostic
+                static const int ctas_per_sm = getenv("TSG_MC_BCAST_CTAS") ? atoi(getenv("TSG_MC_BCAST_CTAS")) : 2;
+                const int grid = num_sms() * (ctas_per_sm > 0 ? ctas_per_sm : 2);
+                if (reinterpret_cast<uintptr_t>(X) & 15)  // a caller's X that is only float-aligned: word stores
+                    k_mc_broadcast_words<<<grid, 512, 0, st>>>(X, D->x_sym_mc, (long long)(xbytes / 4));
+                else if (unroll >= 4)
+                    k_mc_broadcast<4><<<grid, 512, 0, st>>>(reinterpret_cast<const float4 *>(X), D->x_sym_mc, (long long)(xbytes / 16));
+                else
+                    k_mc_broadcast<1><<<grid, 512, 0, st>>>(reinterpret_cast<const float4 *>(X), D->x_sym_mc, (long long)(xbytes / 16));
                 TSG_KERNEL_CHECK("k_mc_broadcast");
             }
             // ordering: the barrier that opens every exchange mode below follows root's kernel in root's stream, so no rank

@@ -124,6 +124,28 @@ def _gpu_worker(rank, world, port_no, q):
             torch.cuda.synchronize()
             out[(mode, M, K, N)] = Y.cpu().numpy().copy()
             dist.barrier()
+        if D.has_multicast():
+            # root's X only float-aligned (and only root's): the choice of broadcast path must not depend on a rank's own pointer
+            flat = torch.zeros(M * K + 1, device="cuda")
+            X = flat[1:].view(M, K) if rank == 0 else flat[:M * K].view(M, K)
+            if rank == 0:
+                X.copy_(t.gen_uniform((M, K), 43))
+            Y = D.alloc_y(M, N)
+            D.gemm(W, X, B, Y, N, a=0.2, use_prelu=True, root=0, mode=5)
+            torch.cuda.synchronize()
+            out[("unaligned_root_x", M, K, N)] = Y.cpu().numpy().copy()
+            out[("unaligned_root_x_bcast", M, K, N)] = X.cpu().numpy().copy()
+            dist.barrier()
+            # X above the size up to which the switch broadcasts it: mode 5 with ncclBroadcast, then back
+            os.environ["TSG_MC_BCAST_MAX_MB"] = "0"
+            X = t.gen_uniform((M, K), 43) if rank == 0 else torch.zeros((M, K), device="cuda")
+            for _ in range(2):
+                D.gemm(W, X, B, Y, N, a=0.2, use_prelu=True, root=0, mode=5)
+            del os.environ["TSG_MC_BCAST_MAX_MB"]
+            D.gemm(W, X, B, Y, N, a=0.2, use_prelu=True, root=0, mode=5)
+            torch.cuda.synchronize()
+            out[("nccl_bcast_mode5", M, K, N)] = Y.cpu().numpy().copy()
+            dist.barrier()
         W.destroy()
     q.put((rank, out))
     dist.barrier()
@@ -168,6 +190,11 @@ def test_two_gpus_bit_exact_every_mode():
                     skipped.append(name)
                     continue
                 assert np.array_equal(Y, Yref), f"mode {mode} ({name}), shape {(M, K, N)}, rank {rank}"
+        for rank, out in res:
+            if ("unaligned_root_x", M, K, N) in out:
+                assert np.array_equal(out[("unaligned_root_x", M, K, N)], Yref), f"unaligned root X, shape {(M, K, N)}, rank {rank}"
+                assert np.array_equal(out[("unaligned_root_x_bcast", M, K, N)], port.gen_uniform((M, K), 43)), "X was not broadcast in place"
+                assert np.array_equal(out[("nccl_bcast_mode5", M, K, N)], Yref), f"mode 5 with ncclBroadcast, shape {(M, K, N)}, rank {rank}"
     print("modes without hardware support on this box:", sorted(set(skipped)))
 
 
