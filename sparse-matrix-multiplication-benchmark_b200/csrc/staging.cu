@@ -152,12 +152,28 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
                                 int N, int K) {
     TSG_TRY(ensure_device());
     cudaStream_t user = stream();
-    static thread_local cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    if (!s_in) {
-        TSG_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        TSG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-        TSG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    // streams and events live across calls, per thread AND per device (a thread that changes device gets a new set)
+    struct Pipe {
+        int device = -1;
+        cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+        cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_k[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+    };
+    static thread_local Pipe pipe;
+    const int dev_now = current_device();
+    if (pipe.device != dev_now) {
+        pipe = Pipe();  // the old device's handles are left to its context
+        TSG_CUDA(cudaStreamCreateWithFlags(&pipe.s_in, cudaStreamNonBlocking));
+        TSG_CUDA(cudaStreamCreateWithFlags(&pipe.s_k, cudaStreamNonBlocking));
+        TSG_CUDA(cudaStreamCreateWithFlags(&pipe.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            TSG_CUDA(cudaEventCreateWithFlags(&pipe.ev_in[i], cudaEventDisableTiming));
+            TSG_CUDA(cudaEventCreateWithFlags(&pipe.ev_k[i], cudaEventDisableTiming));
+            TSG_CUDA(cudaEventCreateWithFlags(&pipe.ev_out[i], cudaEventDisableTiming));
+        }
+        pipe.device = dev_now;
     }
+    cudaStream_t s_in = pipe.s_in, s_k = pipe.s_k, s_out = pipe.s_out;
+    cudaEvent_t *ev_in = pipe.ev_in, *ev_k = pipe.ev_k, *ev_out = pipe.ev_out;
     TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
     // slabs: multiples of 128 rows (the kernel's row tile).  PCIe is the bottleneck of a host-pointer call, so the slabs
     // are kept small (about 256 rows, at most 32 of them; TSG_HOST_SLAB_ROWS overrides): the un-overlapped head (first H2D) and tail (last kernel +
@@ -175,7 +191,6 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     if (saved_kernel == 0 && M >= TSG_SKINNY_M) tsg_tcsc_set_kernel(1);
     const int nbuf = nslab < 3 ? nslab : 3;
     float *dX[3] = {nullptr, nullptr, nullptr}, *dY[3] = {nullptr, nullptr, nullptr}, *dB = nullptr;
-    static thread_local cudaEvent_t ev_in[3] = {nullptr}, ev_k[3] = {nullptr}, ev_out[3] = {nullptr};  // created once per thread
     int rc = TSG_OK;
     tsg_set_stream(s_k);
     int b_owned = 0;
@@ -185,11 +200,6 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     for (int i = 0; i < nbuf && !rc; ++i) {
         rc = dev_alloc_t(&dX[i], (size_t)slab * K);
         if (!rc) rc = dev_alloc_t(&dY[i], (size_t)slab * N);
-        if (!ev_in[i]) {
-            cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
-        }
     }
     if (!rc) rc = build_kstream(W);  // on s_k
     cudaStreamSynchronize(s_k);      // pool allocations above are ordered on s_k; the copy streams use them next
