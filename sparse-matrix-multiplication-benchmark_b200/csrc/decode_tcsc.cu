@@ -47,7 +47,7 @@ __device__ __forceinline__ void dec_accumulate(float (&acc)[MT], const float *xs
 template <int MT>
 __global__ void __launch_bounds__(1024, 1) k_tcsc_decode(const float *__restrict__ X, const int *__restrict__ csp, const int *__restrict__ csn,
                                                          const int *__restrict__ rip, const int *__restrict__ rin, const float *__restrict__ B, float a,
-                                                         int use_prelu, int bias_first, float *__restrict__ Y, long long ldy, int M, int N, int K) {
+                                                         int use_prelu, float *__restrict__ Y, long long ldy, int M, int N, int K) {
     extern __shared__ __align__(16) float xs[];  // [K][MT]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int m0 = blockIdx.y * MT;
@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(1024, 1) k_tcsc_decode(const float *__restrict
         }
         n = nn;
     }
-    (void)bias_first;
 }
 
 // *handled = 0 when the rows of X do not fit shared memory even one at a time (K > ~56 K): the caller falls back
@@ -127,10 +126,10 @@ int tcsc_decode(tsg_tcsc *W, const float *X, const float *B, float a, int use_pr
     dim3 grid(gx, groups);
     cudaStream_t st = stream();
     switch (mt) {
-        case 1: k_tcsc_decode<1><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, 0, Y, ldy, M, N, K); break;
-        case 2: k_tcsc_decode<2><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, 0, Y, ldy, M, N, K); break;
-        case 4: k_tcsc_decode<4><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, 0, Y, ldy, M, N, K); break;
-        default: k_tcsc_decode<8><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, 0, Y, ldy, M, N, K); break;
+        case 1: k_tcsc_decode<1><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        case 2: k_tcsc_decode<2><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        case 4: k_tcsc_decode<4><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
+        default: k_tcsc_decode<8><<<grid, threads, smem, st>>>(X, W->csp, W->csn, W->rip, W->rin, B, a, use_prelu, Y, ldy, M, N, K); break;
     }
     TSG_KERNEL_CHECK("k_tcsc_decode");
     *handled = 1;
