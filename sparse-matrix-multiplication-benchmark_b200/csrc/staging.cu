@@ -92,11 +92,60 @@ int staged_gemm(const float *X, const float *B, float *Y, int M, int N, int K, G
     return rc;
 }
 
+constexpr int kMaxSlabs = 72;
+
+// row slabs of the pipelined host-pointer GEMM (see tsg_shim_tcsc_gemm_hostpipe); uniform_rows > 0 forces uniform slabs
+int host_slab_schedule(int M, int uniform_rows, int *slab_rows) {
+    int nslab = 0;
+    if (M < TSG_SKINNY_M || M <= 256) {
+        slab_rows[nslab++] = M;
+    } else if (uniform_rows > 0) {
+        int n = (M + uniform_rows - 1) / uniform_rows;
+        if (n > 32) n = 32;
+        const int rows = (((M + n - 1) / n) + 127) / 128 * 128;
+        for (int m0 = 0; m0 < M; m0 += rows) slab_rows[nslab++] = (M - m0 < rows) ? (M - m0) : rows;
+    } else {
+        // head: 128, 128, 256, 512 while it stays below half of M; the tail mirrors it; the middle is cut into <= 1024-row slabs
+        int head[4], nh = 0, sum = 0;
+        for (int sz = 128, i = 0; i < 4; ++i) {
+            if (2 * (sum + sz) > M) break;
+            head[nh++] = sz;
+            sum += sz;
+            if (i >= 1) sz *= 2;
+        }
+        const int mid = M - 2 * sum;  // >= 0; a ragged M leaves its odd rows here
+        int cap = 1024;
+        while ((mid + cap - 1) / cap + 2 * nh > kMaxSlabs) cap *= 2;
+        for (int i = 0; i < nh; ++i) slab_rows[nslab++] = head[i];
+        const int nmid = (mid + cap - 1) / cap;
+        for (int i = 0, left = mid; i < nmid; ++i) {
+            int rows = ((left / (nmid - i)) + 127) / 128 * 128;  // equal parts, rounded up to row tiles
+            if (rows > left) rows = left;
+            if (rows > 0) slab_rows[nslab++] = rows;
+            left -= rows;
+        }
+        for (int i = nh - 1; i >= 0; --i) slab_rows[nslab++] = head[i];
+        // the ragged rest of M (fewer than 128 rows) rides with its left neighbour instead of being a slab of its own
+        for (int i = 1; i < nslab; ++i) {
+            if (slab_rows[i] < 128) {
+                slab_rows[i - 1] += slab_rows[i];
+                for (int k = i; k + 1 < nslab; ++k) slab_rows[k] = slab_rows[k + 1];
+                --nslab;
+                --i;
+            }
+        }
+    }
+    return nslab;
+}
+
 }  // namespace
 
 extern "C" {
 
 int tsg_shim_is_device(const void *p) { return is_device_pointer(p); }
+
+// diagnostic (tests/test_plan.py): the slab schedule of the pipelined host-pointer GEMM; out must hold 72 ints
+int tsg_dbg_host_slabs(int M, int uniform_rows, int *out) { return host_slab_schedule(M, uniform_rows, out); }
 
 int tsg_shim_stage_in(const void *p, size_t bytes, void **dev, int *owned) {
     TSG_TRY(ensure_device());
@@ -175,17 +224,16 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     cudaStream_t s_in = pipe.s_in, s_k = pipe.s_k, s_out = pipe.s_out;
     cudaEvent_t *ev_in = pipe.ev_in, *ev_k = pipe.ev_k, *ev_out = pipe.ev_out;
     TSG_CUDA(cudaStreamSynchronize(user));  // W's mirror may have been built on the user stream
-    // slabs: multiples of 128 rows (the kernel's row tile).  PCIe is the bottleneck of a host-pointer call, so the slabs
-    // are kept small (about 256 rows, at most 32 of them; TSG_HOST_SLAB_ROWS overrides): the un-overlapped head (first H2D) and tail (last kernel +
-    // last D2H) shrink with the slab, and the kernel's lower efficiency on small slabs hides under the copies
-    int slab_rows = 256;
-    if (const char *e = getenv("TSG_HOST_SLAB_ROWS")) slab_rows = atoi(e) > 0 ? atoi(e) : 256;
-    int nslab = (M + slab_rows - 1) / slab_rows;
-    if (nslab > 32) nslab = 32;
-    if (nslab < 4) nslab = (M + 127) / 128 < 4 ? (M + 127) / 128 : 4;
-    int slab = (((M + nslab - 1) / nslab) + 127) / 128 * 128;
-    if (M < TSG_SKINNY_M) slab = M;
-    nslab = (M + slab - 1) / slab;
+    // Slabs are multiples of 128 rows (the kernel's row tile).  PCIe is the bottleneck of a host-pointer call and the GEMM on a
+    // short slab runs at a fraction of its large-M efficiency, so the schedule is a RAMP: 128-row slabs at both ends (the
+    // un-overlapped head -- first H2D -- and tail -- last kernel + last D2H -- shrink with the slab) doubling towards
+    // 1024-row slabs in the middle (where the kernel must not become the longest leg).  TSG_HOST_SLAB_ROWS=n forces uniform
+    // n-row slabs (at most 32 of them), the round-1 schedule.
+    int slab_rows[kMaxSlabs];
+    const char *env_slab = getenv("TSG_HOST_SLAB_ROWS");
+    const int nslab = host_slab_schedule(M, env_slab ? atoi(env_slab) : 0, slab_rows);
+    int slab = 0;  // the largest one (buffer size)
+    for (int i = 0; i < nslab; ++i) slab = slab_rows[i] > slab ? slab_rows[i] : slab;
     // one call = one kernel family: a short last slab must not drop into the skinny kernel (different summation order)
     const int saved_kernel = tsg_tcsc_get_kernel();
     if (saved_kernel == 0 && M >= TSG_SKINNY_M) tsg_tcsc_set_kernel(1);
@@ -204,9 +252,9 @@ int tsg_shim_tcsc_gemm_hostpipe(tsg_tcsc *W, const float *X, const float *B_any,
     if (!rc) rc = build_kstream(W);  // on s_k
     cudaStreamSynchronize(s_k);      // pool allocations above are ordered on s_k; the copy streams use them next
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < nslab && !rc && e == cudaSuccess; ++i) {
+    for (int i = 0, m0 = 0; i < nslab && !rc && e == cudaSuccess; m0 += slab_rows[i], ++i) {
         const int b = i % nbuf;
-        const int m0 = i * slab, rows = (M - m0 < slab) ? (M - m0) : slab;
+        const int rows = slab_rows[i];
         if (i >= nbuf) {  // buffer reuse: the kernel that read dX[b] and the copy that drained dY[b] must be done
             e = cudaStreamWaitEvent(s_in, ev_k[b], 0);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, ev_out[b], 0);

@@ -102,3 +102,23 @@ def test_bcsr_ring_plan_never_lengthens_the_last_round(L, units, sms, bpw):
     assert rounds_split <= rounds_plain
     if bpw >= 2 and 0 < units % sms <= sms // 2:
         assert sub == 2 and rounds_split == rounds_plain - 0.5
+
+
+@pytest.mark.parametrize("M", [1, 31, 32, 100, 256, 257, 384, 511, 512, 600, 1024, 2048, 4096, 5000, 8192, 16384, 65536, 100000, 200001])
+def test_host_slab_schedule_covers_all_rows(L, M):
+    """staging.cu: the pipelined host-pointer GEMM cuts M into a ramp of slabs (128 rows at both ends, up to 1024+ in the middle)."""
+    out = (C.c_int * 72)()
+    L.tsg_dbg_host_slabs.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int * 72)]
+    n = L.tsg_dbg_host_slabs(M, 0, C.byref(out))
+    v = list(out)[:n]
+    assert 1 <= n <= 72 and sum(v) == M and all(x > 0 for x in v)
+    if M > 256:
+        assert all(x >= 128 for x in v), v                       # no sliver slabs
+        assert v[0] <= 255 and v[-1] <= 255                      # short head and tail
+        assert sum(1 for x in v if x % 128) <= 1                 # only the ragged rest is not a whole number of row tiles
+    else:
+        assert v == [M]
+    # the forced uniform schedule (TSG_HOST_SLAB_ROWS)
+    n = L.tsg_dbg_host_slabs(M, 256, C.byref(out))
+    u = list(out)[:n]
+    assert sum(u) == M and all(x > 0 for x in u) and n <= 32
