@@ -10,8 +10,10 @@
  *   - b_row_start is a standard CSR pointer array (br+1 entries, empty block-rows repeat the previous value).  The
  *     reference only appends an entry for block-rows that own a block (bcsr.c:114-117) and leaves the tail
  *     uninitialised; both agree whenever no block-row is empty.
- *   - bcsr_sgemm_prelu_* return PReLU(X*W + B) with PReLU(y) = y<0 ? a*y : y.  The reference applies the activation
- *     after every partial update (bcsr.c:208-212, 300-306), which is not that function.
+ *   - bcsr_sgemm_prelu_* return PReLU(X*W + B) with PReLU(y) = y<0 ? a*y : y by default.  The reference applies the
+ *     activation after every partial update (bcsr.c:208-212, 300-306), which is not that function;
+ *     tsg_bcsr_set_prelu_literal(1) (tsgemm_b200.h) or TSG_BCSR_PRELU_LITERAL=1 makes these two entry points return the
+ *     reference's literal result instead, bit for bit.
  *   - the *_avx / *_avx2 names are aliases of the one CUDA kernel; their alignment and c==8 / r==c==8
  *     preconditions (bcsr.c:229-230, 316) are not required here.
  * The __restrict qualifier on the by-value struct parameter of the reference prototypes is a g++-ism with no ABI

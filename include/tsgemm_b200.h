@@ -112,8 +112,14 @@ int tsg_bcsr_from_arrays(const int *b_row_start, const int *b_col_idx, const flo
 void tsg_bcsr_destroy(tsg_bcsr *W);
 int tsg_bcsr_dims(const tsg_bcsr *W, int *r, int *c, int *br, int *bc, int *k);
 int tsg_bcsr_download(const tsg_bcsr *W, int *b_row_start, int *b_col_idx, float *b_values);
+/* use_prelu: 0 = none, 1 = PReLU(X*W + B), 2 = the reference's literal bcsr_sgemm_prelu_* loop (activation after every
+ * partial update, untouched outputs keep the raw bias: sparse/bcsr.c:177-218, 264-312), bit-identical to it. */
 int tsg_bcsr_gemm(tsg_bcsr *W, const float *X_dev, const float *B_dev, float a, int use_prelu, float *Y_dev,
                   int M, int N, int K, long long ldy);
+/* what the reference-named bcsr_sgemm_prelu_basic / _avx compute on this thread: 0 (default, also TSG_BCSR_PRELU_LITERAL
+ * unset) = PReLU(X*W + B); 1 = the reference's literal loop, for callers that need its exact output. */
+int tsg_bcsr_set_prelu_literal(int on);
+int tsg_bcsr_get_prelu_literal(void);
 /* kernel selection for A/B runs: 0 = default (the shared-memory ring kernel; the plain kernel when TSG_BCSR_RING=0 is
  * set), 1 = plain kernel, 2 = ring kernel (falls back to the plain one outside its limits: c not in {1,2,4,8,16},
  * r > 224).  Both produce the same bits. */

@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     L.tsg_bcsr_download.argtypes = [vp, vp, vp, vp]
     L.tsg_bcsr_gemm.argtypes = [vp, vp, vp, f, i, vp, i, i, i, ll]
     L.tsg_bcsr_set_kernel.argtypes = [i]
+    L.tsg_bcsr_set_prelu_literal.argtypes = [i]
+    L.tsg_bcsr_get_prelu_literal.argtypes = []
     L.tsg_gen_ternary_f32.argtypes = [vp, ll, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_ternary_i32.argtypes = [vp, ll, C.c_uint64, C.c_uint32, C.c_uint32]
     L.tsg_gen_ternary_slice_f32.argtypes = [vp, i, i, i, i, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -397,6 +399,12 @@ def bcsr_sgemm_prelu_basic(X, W, B, a, N, Y=None):
 
 def bcsr_sgemm_prelu_avx(X, W, B, a, N, Y=None):
     return _bgemm("bcsr_sgemm_prelu_avx", X, W, B, a, Y, N)
+
+
+def bcsr_set_prelu_literal(on: bool) -> None:
+    """bcsr_sgemm_prelu_basic / _avx on this thread: False (default) = PReLU(X*W + B); True = the reference's literal loop
+    (activation after every partial update, sparse/bcsr.c:177-218), bit-identical to the reference."""
+    _check(lib().tsg_bcsr_set_prelu_literal(1 if on else 0), "tsg_bcsr_set_prelu_literal")
 
 
 def bcsr_set_kernel(which: int) -> None:

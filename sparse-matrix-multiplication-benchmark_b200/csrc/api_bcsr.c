@@ -162,14 +162,15 @@ static void run_bcsr(const float *X, const bcsr_t *W, const float *B, float a, i
 void bcsr_sgemm_basic(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
     run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);
 }
+/* 1 = PReLU(X*W + B); 2 = the reference's literal loop (bcsr.c:177-218, 264-312), opted into with tsg_bcsr_set_prelu_literal(1) */
 void bcsr_sgemm_prelu_basic(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, float a, dense_t __restrict Y, int M, int N, int K) {
-    run_bcsr(X, &W, B, a, 1, Y, M, N, K);
+    run_bcsr(X, &W, B, a, tsg_bcsr_get_prelu_literal() ? 2 : 1, Y, M, N, K);
 }
 void bcsr_sgemm_avx(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
     run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);
 }
 void bcsr_sgemm_prelu_avx(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, float a, dense_t __restrict Y, int M, int N, int K) {
-    run_bcsr(X, &W, B, a, 1, Y, M, N, K);
+    run_bcsr(X, &W, B, a, tsg_bcsr_get_prelu_literal() ? 2 : 1, Y, M, N, K);
 }
 void bcsr_sgemm_avx2(const dense_t __restrict X, const bcsr_t W, const dense_t __restrict B, dense_t __restrict Y, int M, int N, int K) {
     run_bcsr(X, &W, B, 0.0f, 0, Y, M, N, K);

@@ -3,7 +3,9 @@
 Bars: b_row_start / b_col_idx bit-exact and b_values bit-exact against the reference's golden vectors (every golden
 case has no empty block-row, where the reference's row pointers are well defined); Y of bcsr_sgemm_basic / _avx /
 _avx2 bit-exact against the oracle (ascending-k accumulation from the bias, one rounding per term, ternary blocks =>
-x*val exact); bcsr_sgemm_prelu_* equal PReLU of that, i.e. the north-star math, not the reference's literal loop.
+x*val exact); bcsr_sgemm_prelu_* equal PReLU of that, i.e. the north-star math, by default -- and the reference's literal
+loop (activation after every partial update), bit for bit against the unmodified reference's outputs, after
+tsg_bcsr_set_prelu_literal(1).
 Decode shapes (M < 32, block width 4/8/16) run the tree-summing decode kernel by default (csrc/decode_bcsr.cu): there the bar is
 the tolerance contract, max |y - y_exact| <= 1e-5 * max(|y_exact|, 1), with the bit-exact kernels (tsg_bcsr_set_kernel(2))
 checked next to it on the same inputs."""
@@ -75,7 +77,14 @@ def test_bcsr_golden(t, port, golden, case):
         # the reference's literal prelu loop returns something else: reported, not matched
         lit = golden[f"bcsr.{name}.real.prelu_basic_literal"]
         print(f"{name}: max |PReLU(X*W+b) - reference literal loop| = {np.abs(yp - lit).max():.3e}")
+        # ... and is reproduced bit for bit on request (tsg_bcsr_set_prelu_literal; outputs of the UNMODIFIED reference)
+        t.bcsr_set_prelu_literal(True)
+        assert np.array_equal(t.bcsr_sgemm_prelu_basic(Xu, w, Bu, 0.2, N), lit)
+        if c == 8:
+            assert np.array_equal(t.bcsr_sgemm_prelu_avx(Xu, w, Bu, 0.2, N), golden[f"bcsr.{name}.real.prelu_avx_literal"])
+        assert np.array_equal(t.bcsr_sgemm_basic(Xu, w, Bu, N), y)  # the switch touches the prelu entry points only
     finally:
+        t.bcsr_set_prelu_literal(False)
         t.bcsr_set_kernel(0)
         w.free()
 
@@ -101,7 +110,14 @@ def test_bcsr_vs_oracle(t, port, shape):
         y = t.bcsr_sgemm_basic(X, w, B, N)
         assert np.array_equal(y, port.bcsr_sgemm_basic(X, wo, B, N))
         assert np.array_equal(t.bcsr_sgemm_prelu_basic(X, w, B, 0.2, N), port.bcsr_sgemm_prelu_math(X, wo, B, 0.2, N))
+        # the reference's literal loop (bcsr.c:177-218) on request: sequential per output, bit-exact against its restatement,
+        # including generic block widths, dropped remainder columns (raw bias) and empty block-rows
+        t.bcsr_set_kernel(0)
+        t.bcsr_set_prelu_literal(True)
+        assert np.array_equal(t.bcsr_sgemm_prelu_basic(X, w, B, 0.2, N), port.bcsr_sgemm_prelu_literal(X, wo, B, 0.2, N))
+        assert np.array_equal(t.bcsr_sgemm_prelu_avx(X, w, B, -0.5, N), port.bcsr_sgemm_prelu_literal(X, wo, B, -0.5, N))
     finally:
+        t.bcsr_set_prelu_literal(False)
         t.bcsr_set_kernel(0)
         w.free()
 
